@@ -1,0 +1,160 @@
+"""Host-side mirror of the reference's cp-groth16 operator interface for the hot path, over the
+C ABI.  Same names, argument meaning and error behaviour as the Rust (the tests read like
+cp-groth16/src/lib.rs:139-180):
+
+    reference (Rust)                                   here
+    -------------------------------------------------  -----------------------------------------
+    ProvingKey<E>            data_structures.rs:66-83  ProvingKey (device-resident base sets)
+    MultiStageConstraintSystem                          StagedAssignment (matrices + assignment +
+        constraint_synthesizer.rs:14-117                   per-stage witness ranges)
+    CommitmentBuilder::new   committer.rs:38-52        CommitmentBuilder(assignment, pk)
+    CommitmentBuilder::commit  committer.rs:55-98      .commit(rng | kappa=)
+    CommitmentBuilder::prove   committer.rs:100-122    .prove(comms, comm_rands, rng | r=, s=)
+    Proof{a,b,c,ds}          data_structures.rs:7-16   Proof
+
+Constraint synthesis (gadgets) is outside the hot path and stays on the host: a
+StagedAssignment is what `generate_constraints` + `cs.finalize()` leave behind.  Randomness is
+drawn on the host in the reference's order (kappa in commit: committer.rs:85; r then s in
+prove: prover.rs:28-29); the device never sees an RNG.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import codec
+from .backend import SCALAR_MONT
+
+
+@dataclass
+class Proof:
+    a: tuple
+    b: tuple
+    c: tuple
+    ds: list = field(default_factory=list)
+
+
+class StagedAssignment:
+    """Matrices in CSR (columns over [instance || witness]), the assignment, and the witness
+    range of every stage (constraint_synthesizer.rs:21,53-64,96-106)."""
+
+    def __init__(self, curve, num_instance, a_rows, b_rows, c_rows, instance, witness, stage_ranges):
+        self.curve = curve
+        self.l = num_instance
+        self.rows = (a_rows, b_rows, c_rows)
+        self.instance = list(instance)
+        self.witness = list(witness)
+        self.stage_ranges = list(stage_ranges)
+        assert len(self.instance) == self.l and self.instance[0] == 1
+        for (s0, e0), (s1, _) in zip(self.stage_ranges, self.stage_ranges[1:]):
+            assert e0 == s1, "stage witness ranges must be contiguous"
+
+    @classmethod
+    def from_circuit(cls, circ, curve):
+        """Adopt a circuit object exposing .r1cs{num_instance,a,b,c}, .instance, .witness, .stage_ranges."""
+        from .curves import get_curve
+        r1 = circ.r1cs
+        return cls(get_curve(curve), r1.num_instance, r1.a, r1.b, r1.c, circ.instance, circ.witness,
+                   circ.stage_ranges)
+
+    @property
+    def num_constraints(self):
+        return len(self.rows[0])
+
+    def full_assignment(self):
+        return self.instance + self.witness
+
+    def csr(self):
+        r = self.curve.r
+        out = []
+        for rows in self.rows:
+            ptr = np.zeros(len(rows) + 1, dtype=np.uint32)
+            cols, vals = [], []
+            for i, row in enumerate(rows):
+                for cf, j in row:
+                    cols.append(j)
+                    vals.append(cf % r)
+                ptr[i + 1] = len(cols)
+            out.append((ptr, np.array(cols, dtype=np.uint32), codec.to_mont(vals, r, 4) if vals
+                        else np.zeros((0, 4), dtype=np.uint64)))
+        return out
+
+
+class ProvingKey:
+    """Device-resident proving key: every vector of data_structures.rs:66-114 is uploaded once."""
+
+    def __init__(self, ctx, handle, num_stages, l, nw, log_n, vk=None):
+        self.ctx, self.handle, self.num_stages, self.l, self.nw, self.log_n = ctx, handle, num_stages, l, nw, log_n
+        self.vk = vk
+
+    @classmethod
+    def from_points(cls, ctx, staged, a_g, b_g, b_h, h_g, deltas_abc_g, deltas_g, alpha_g, beta_g, beta_h,
+                    last_delta_h):
+        cv = ctx.curve
+        up1 = lambda pts: ctx.upload_g1(*codec.g1_affine_to_limbs(pts, cv))
+        up2 = lambda pts: ctx.upload_g2(*codec.g2_affine_to_limbs(pts, cv))
+        h_a, h_b1, h_b2, h_h = up1(a_g), up1(b_g), up2(b_h), up1(h_g)
+        h_ck = [up1(v) for v in deltas_abc_g]
+        h_d = up1(deltas_g)
+        return cls.from_handles(ctx, staged, h_a, h_b1, h_h, h_b2, h_ck, h_d, alpha_g, beta_g, beta_h, last_delta_h)
+
+    @classmethod
+    def from_handles(cls, ctx, staged, h_a, h_b1, h_h, h_b2, h_ck, h_d, alpha_g, beta_g, beta_h, last_delta_h):
+        cv = ctx.curve
+        n = staged.num_constraints
+        nw = len(staged.witness)
+        r1 = ctx.r1cs_upload(n, staged.l, nw, staged.csr())
+        starts = [s for s, _ in staged.stage_ranges] + [staged.stage_ranges[-1][1]]
+        pk = ctx.pk_create(h_a, h_b1, h_h, h_b2, h_ck, h_d,
+                           codec.g1_affine_to_limbs([alpha_g], cv)[0], codec.g1_affine_to_limbs([beta_g], cv)[0],
+                           codec.g2_affine_to_limbs([beta_h], cv)[0], codec.g2_affine_to_limbs([last_delta_h], cv)[0],
+                           r1, starts)
+        log_n = max(1, (n + staged.l - 1).bit_length())
+        return cls(ctx, pk, len(h_ck), staged.l, nw, log_n)
+
+    @classmethod
+    def from_key(cls, ctx, opk, circ):
+        staged = StagedAssignment.from_circuit(circ, ctx.curve)
+        return cls.from_points(ctx, staged, opk.a_g, opk.b_g, opk.b_h, opk.h_g, opk.deltas_abc_g, opk.deltas_g,
+                               opk.alpha_g, opk.beta_g, opk.beta_h, opk.last_delta_h)
+
+
+class CommitmentBuilder:
+    """committer.rs:15-122.  `assignment` plays the role of (circuit, cs) after synthesis."""
+
+    def __init__(self, assignment, pk):
+        self.cs = assignment
+        self.pk = pk
+        self.cur_stage = 0
+        cv = pk.ctx.curve
+        self._z = codec.to_mont(assignment.full_assignment(), cv.r, 4)
+
+    def _fr(self, v):
+        return codec.to_mont([v], self.pk.ctx.curve.r, 4)[0]
+
+    def commit(self, rng=None, kappa=None):
+        """-> (Comm, CommRandomness).  Raises like the reference's `expect` when no stage is left."""
+        if self.cur_stage >= self.pk.num_stages:
+            raise IndexError("no more values left in committing key")
+        if kappa is None:
+            kappa = rng.fr_rand()
+        ctx = self.pk.ctx
+        out, inf = ctx.commit(self.pk.handle, self.cur_stage, self._z, self._fr(kappa))
+        self.cur_stage += 1
+        com = None if inf else codec.g1_affine_from_limbs(out, ctx.curve)[0]
+        return com, kappa
+
+    def prove(self, comms, comm_rands, rng=None, r=None, s=None):
+        """committer.rs:100-122: requires deltas_g.len() == comm_rands.len() + 1."""
+        assert self.pk.num_stages == len(comm_rands) + 1, "deltas_g.len() must equal comm_rands.len() + 1"
+        if r is None:
+            r = rng.fr_rand()
+        if s is None:
+            s = rng.fr_rand()
+        ctx = self.pk.ctx
+        cv = ctx.curve
+        kap = codec.to_mont(list(comm_rands), cv.r, 4) if comm_rands else np.zeros((0, 4), dtype=np.uint64)
+        a, b, c, inf = ctx.prove(self.pk.handle, self._z, self._fr(r), self._fr(s), kap)
+        A = None if inf[0] else codec.g1_affine_from_limbs(a, cv)[0]
+        B = None if inf[1] else codec.g2_affine_from_limbs(b, cv)[0]
+        Cc = None if inf[2] else codec.g1_affine_from_limbs(c, cv)[0]
+        return Proof(A, B, Cc, list(comms))

@@ -1,0 +1,642 @@
+// extern "C" surface of libhekaton_b200.so (declared in include/hekaton_b200.h).
+// Host pointers are staged through context-owned device buffers; device pointers are used in
+// place.  There is no CPU compute path anywhere in this file.
+#include <chrono>
+
+#include "common.cuh"
+#include "prove.cuh"
+#include "qap.cuh"
+
+using namespace hk;
+
+#define HK_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+template <class Fn1, class Fn2>
+void by_curve(hk_ctx* ctx, Fn1&& bls, Fn2&& bn) {
+    if (ctx->curve == HK_CURVE_BLS12_381) bls();
+    else bn();
+}
+
+size_t fq_bytes(const hk_ctx* ctx) { return ctx->curve == HK_CURVE_BLS12_381 ? 48 : 32; }
+size_t point_bytes(const hk_ctx* ctx, int group) { return fq_bytes(ctx) * 2 * (group == 2 ? 2 : 1); }
+size_t jac_bytes(const hk_ctx* ctx, int group) { return fq_bytes(ctx) * 3 * (group == 2 ? 2 : 1); }
+
+// stage `bytes` from host (via pinned memory) or alias a device pointer
+const void* to_device(hk_ctx* ctx, DevBuf& buf, const void* p, size_t bytes, uint32_t memspace) {
+    if (memspace == HK_DEVICE || bytes == 0) return p;
+    void* d = buf.ensure(bytes);
+    HK_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return d;
+}
+
+uint64_t new_handle(hk_ctx* ctx) { return ctx->next_handle++; }
+
+BaseSet& find_bases(hk_ctx* ctx, uint64_t h, int group) {
+    auto it = ctx->bases.find(h);
+    HK_REQUIRE(it != ctx->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
+    HK_REQUIRE(it->second->group == group, HK_ERR_INVALID, "base set belongs to the other group");
+    return *it->second;
+}
+
+void bases_upload(hk_ctx* ctx, int group, const void* pts, const uint8_t* inf, size_t n, uint32_t memspace,
+                  uint64_t* handle) {
+    HK_REQUIRE(handle, HK_ERR_INVALID, "handle is NULL");
+    HK_REQUIRE(pts || n == 0, HK_ERR_INVALID, "points pointer is NULL");
+    auto bs = std::make_unique<BaseSet>();
+    bs->group = group;
+    bs->n = n;
+    bs->point_bytes = point_bytes(ctx, group);
+    size_t bytes = n * bs->point_bytes;
+    cudaError_t e = cudaMalloc(&bs->d, bytes + 256);
+    if (e != cudaSuccess) throw HkError{HK_ERR_NOMEM, std::string("cudaMalloc bases: ") + cudaGetErrorString(e)};
+    if (bytes)
+        HK_CUDA(cudaMemcpyAsync(bs->d, pts, bytes, memspace == HK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                ctx->stream));
+    if (inf && n) {
+        const uint8_t* d_inf = (const uint8_t*)to_device(ctx, ctx->ws_io[3], inf, n, memspace);
+        by_curve(ctx, [&] { apply_infinity<Bls12381>(ctx, *bs, d_inf); }, [&] { apply_infinity<Bn254>(ctx, *bs, d_inf); });
+    }
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t h = new_handle(ctx);
+    ctx->bases[h] = std::move(bs);
+    *handle = h;
+}
+
+void bases_from_scalars(hk_ctx* ctx, int group, const void* gen, const uint64_t* scalars, size_t n, uint32_t repr,
+                        uint32_t memspace, uint64_t* handle) {
+    HK_REQUIRE(handle && gen, HK_ERR_INVALID, "NULL argument");
+    auto bs = std::make_unique<BaseSet>();
+    bs->group = group;
+    bs->n = n;
+    bs->point_bytes = point_bytes(ctx, group);
+    cudaError_t e = cudaMalloc(&bs->d, n * bs->point_bytes + 256);
+    if (e != cudaSuccess) throw HkError{HK_ERR_NOMEM, std::string("cudaMalloc bases: ") + cudaGetErrorString(e)};
+    const void* d_gen = to_device(ctx, ctx->ws_io[2], gen, bs->point_bytes, HK_HOST);
+    const Scalar256* d_sc = (const Scalar256*)to_device(ctx, ctx->ws_io[0], scalars, n * 32, memspace);
+    bool mont = repr == HK_SCALAR_MONT;
+    if (group == 1)
+        by_curve(ctx, [&] { fixed_base_mul<Bls12381, 1>(ctx, d_gen, d_sc, n, mont, bs->d); },
+                 [&] { fixed_base_mul<Bn254, 1>(ctx, d_gen, d_sc, n, mont, bs->d); });
+    else
+        by_curve(ctx, [&] { fixed_base_mul<Bls12381, 2>(ctx, d_gen, d_sc, n, mont, bs->d); },
+                 [&] { fixed_base_mul<Bn254, 2>(ctx, d_gen, d_sc, n, mont, bs->d); });
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t h = new_handle(ctx);
+    ctx->bases[h] = std::move(bs);
+    *handle = h;
+}
+
+void msm_entry(hk_ctx* ctx, int group, uint64_t bases, size_t base_offset, const uint64_t* scalars, size_t n, size_t K,
+               uint32_t repr, uint32_t memspace, void* out) {
+    HK_REQUIRE(out, HK_ERR_INVALID, "out is NULL");
+    HK_REQUIRE(scalars || n == 0, HK_ERR_INVALID, "scalars is NULL");
+    HK_REQUIRE(repr == HK_SCALAR_BIGINT || repr == HK_SCALAR_MONT, HK_ERR_INVALID, "bad scalar_repr");
+    BaseSet& bs = find_bases(ctx, bases, group);
+    // msm_unchecked / msm_bigint zip to the shorter of (bases, scalars)
+    size_t avail = base_offset < bs.n ? bs.n - base_offset : 0;
+    size_t len = n < avail ? n : avail;
+    const size_t jb = jac_bytes(ctx, group);
+    const Scalar256* d_sc;
+    if (memspace == HK_DEVICE || n == 0) {
+        d_sc = (const Scalar256*)scalars;
+        HK_REQUIRE(len == n || K == 1, HK_ERR_UNSUPPORTED, "batched msm with truncated length needs K == 1");
+    } else {
+        // copy only the used prefix of each vector
+        Scalar256* d = ctx->ws_io[0].as<Scalar256>(len * K + 1);
+        for (size_t k = 0; k < K; k++)
+            if (len)
+                HK_CUDA(cudaMemcpyAsync(d + k * len, (const Scalar256*)scalars + k * n, len * 32, cudaMemcpyHostToDevice,
+                                        ctx->stream));
+        d_sc = d;
+    }
+    void* d_out = (memspace == HK_DEVICE) ? out : ctx->ws_out.ensure(jb * K + 64);
+    const char* d_b = (const char*)bs.d + base_offset * bs.point_bytes;
+    bool mont = repr == HK_SCALAR_MONT;
+    if (group == 1)
+        by_curve(ctx, [&] { msm_run<Bls12381, 1>(ctx, d_b, len, d_sc, K, mont, d_out); },
+                 [&] { msm_run<Bn254, 1>(ctx, d_b, len, d_sc, K, mont, d_out); });
+    else
+        by_curve(ctx, [&] { msm_run<Bls12381, 2>(ctx, d_b, len, d_sc, K, mont, d_out); },
+                 [&] { msm_run<Bn254, 2>(ctx, d_b, len, d_sc, K, mont, d_out); });
+    if (memspace != HK_DEVICE) {
+        HK_CUDA(cudaMemcpyAsync(out, d_out, jb * K, cudaMemcpyDeviceToHost, ctx->stream));
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+}
+
+void into_affine_entry(hk_ctx* ctx, int group, const void* jac, size_t n, void* out_xy, uint8_t* inf_out) {
+    HK_REQUIRE(jac && out_xy, HK_ERR_INVALID, "NULL argument");
+    if (n == 0) return;
+    const size_t jb = jac_bytes(ctx, group), pb = point_bytes(ctx, group);
+    const void* d_j = to_device(ctx, ctx->ws_io[0], jac, jb * n, HK_HOST);
+    char* d_o = (char*)ctx->ws_io[1].ensure(pb * n + n + 64);
+    uint8_t* d_inf = (uint8_t*)(d_o + pb * n);
+    if (group == 1)
+        by_curve(ctx, [&] { jac_to_affine<Bls12381, 1>(ctx, d_j, d_o, d_inf, n); },
+                 [&] { jac_to_affine<Bn254, 1>(ctx, d_j, d_o, d_inf, n); });
+    else
+        by_curve(ctx, [&] { jac_to_affine<Bls12381, 2>(ctx, d_j, d_o, d_inf, n); },
+                 [&] { jac_to_affine<Bn254, 2>(ctx, d_j, d_o, d_inf, n); });
+    HK_CUDA(cudaMemcpyAsync(out_xy, d_o, pb * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (inf_out) HK_CUDA(cudaMemcpyAsync(inf_out, d_inf, n, cudaMemcpyDeviceToHost, ctx->stream));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- element-wise field ops (test hook) ---------------------------------------------------------
+template <class F>
+__global__ void k_field_op(const F* a, const F* b, F* out, size_t n, uint32_t op) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = a[i];
+    F r;
+    switch (op) {
+        case HK_FOP_MUL: r = x * b[i]; break;
+        case HK_FOP_ADD: r = x + b[i]; break;
+        case HK_FOP_SUB: r = x - b[i]; break;
+        case HK_FOP_INV: r = x.inverse(); break;
+        case HK_FOP_TO_MONT: r = x.to_mont(); break;
+        default: r = x.from_mont(); break;
+    }
+    out[i] = r;
+}
+
+template <class F>
+void field_op_run(hk_ctx* ctx, uint32_t op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    size_t bytes = n * sizeof(F);
+    const F* da = (const F*)to_device(ctx, ctx->ws_io[0], a, bytes, HK_HOST);
+    const F* db = b ? (const F*)to_device(ctx, ctx->ws_io[1], b, bytes, HK_HOST) : da;
+    F* dout = ctx->ws_io[2].as<F>(n + 1);
+    k_field_op<F><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(da, db, dout, n, op);
+    HK_LAUNCH_CHECK(ctx);
+    HK_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+// ---- throughput probes ---------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) k_bench_mul(F* out, uint32_t iters) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    F x = F::zero(), y = F::zero();
+    x.r.v[0] = (i & 0xffff) + 2;   // small values are valid (non-canonical-looking but < p) Montgomery residues
+    y.r.v[0] = (i & 0xfff) + 3;
+    // two independent chains
+    for (uint32_t k = 0; k < iters; k += 2) {
+        x = x * x;
+        y = y * y;
+    }
+    out[i] = x + y;
+}
+
+__global__ void __launch_bounds__(256) k_bench_imad_wide(uint64_t* out, uint32_t iters) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a = tid * 2654435761u + 1, b = tid ^ 0x9e3779b9u;
+    uint64_t c0 = tid, c1 = tid + 1, c2 = tid + 2, c3 = tid + 3, c4 = tid + 4, c5 = tid + 5, c6 = tid + 6, c7 = tid + 7;
+    for (uint32_t k = 0; k < iters; k++) {
+        // 8 independent 4-long carry chains worth of wide multiply-accumulates = 32 per iteration
+        asm volatile(
+            "{\n\t.reg .u64 t0,t1,t2,t3,t4,t5,t6,t7;\n\t"
+            "mul.wide.u32 t0, %8, %9;\n\t mul.wide.u32 t1, %9, %9;\n\t mul.wide.u32 t2, %8, %8;\n\t mul.wide.u32 t3, %9, %8;\n\t"
+            "add.cc.u64 %0, %0, t0;\n\t addc.cc.u64 %1, %1, t1;\n\t addc.cc.u64 %2, %2, t2;\n\t addc.u64 %3, %3, t3;\n\t"
+            "mul.wide.u32 t4, %8, %9;\n\t mul.wide.u32 t5, %9, %9;\n\t mul.wide.u32 t6, %8, %8;\n\t mul.wide.u32 t7, %9, %8;\n\t"
+            "add.cc.u64 %4, %4, t4;\n\t addc.cc.u64 %5, %5, t5;\n\t addc.cc.u64 %6, %6, t6;\n\t addc.u64 %7, %7, t7;\n\t"
+            "mul.wide.u32 t0, %8, %9;\n\t mul.wide.u32 t1, %9, %9;\n\t mul.wide.u32 t2, %8, %8;\n\t mul.wide.u32 t3, %9, %8;\n\t"
+            "add.cc.u64 %1, %1, t0;\n\t addc.cc.u64 %2, %2, t1;\n\t addc.cc.u64 %3, %3, t2;\n\t addc.u64 %0, %0, t3;\n\t"
+            "mul.wide.u32 t4, %8, %9;\n\t mul.wide.u32 t5, %9, %9;\n\t mul.wide.u32 t6, %8, %8;\n\t mul.wide.u32 t7, %9, %8;\n\t"
+            "add.cc.u64 %5, %5, t4;\n\t addc.cc.u64 %6, %6, t5;\n\t addc.cc.u64 %7, %7, t6;\n\t addc.u64 %4, %4, t7;\n\t"
+            "mul.wide.u32 t0, %8, %9;\n\t mul.wide.u32 t1, %9, %9;\n\t mul.wide.u32 t2, %8, %8;\n\t mul.wide.u32 t3, %9, %8;\n\t"
+            "add.cc.u64 %2, %2, t0;\n\t addc.cc.u64 %3, %3, t1;\n\t addc.cc.u64 %0, %0, t2;\n\t addc.u64 %1, %1, t3;\n\t"
+            "mul.wide.u32 t4, %8, %9;\n\t mul.wide.u32 t5, %9, %9;\n\t mul.wide.u32 t6, %8, %8;\n\t mul.wide.u32 t7, %9, %8;\n\t"
+            "add.cc.u64 %6, %6, t4;\n\t addc.cc.u64 %7, %7, t5;\n\t addc.cc.u64 %4, %4, t6;\n\t addc.u64 %5, %5, t7;\n\t"
+            "mul.wide.u32 t0, %8, %9;\n\t mul.wide.u32 t1, %9, %9;\n\t mul.wide.u32 t2, %8, %8;\n\t mul.wide.u32 t3, %9, %8;\n\t"
+            "add.cc.u64 %3, %3, t0;\n\t addc.cc.u64 %0, %0, t1;\n\t addc.cc.u64 %1, %1, t2;\n\t addc.u64 %2, %2, t3;\n\t"
+            "mul.wide.u32 t4, %8, %9;\n\t mul.wide.u32 t5, %9, %9;\n\t mul.wide.u32 t6, %8, %8;\n\t mul.wide.u32 t7, %9, %8;\n\t"
+            "add.cc.u64 %7, %7, t4;\n\t addc.cc.u64 %4, %4, t5;\n\t addc.cc.u64 %5, %5, t6;\n\t addc.u64 %6, %6, t7;\n\t"
+            "}"
+            : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7)
+            : "r"(a), "r"(b));
+    }
+    out[tid] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+}
+
+template <class Fn>
+float time_ms(hk_ctx* ctx, Fn&& fn) {
+    cudaEvent_t e0, e1;
+    HK_CUDA(cudaEventCreate(&e0));
+    HK_CUDA(cudaEventCreate(&e1));
+    HK_CUDA(cudaEventRecord(e0, ctx->stream));
+    fn();
+    HK_CUDA(cudaEventRecord(e1, ctx->stream));
+    HK_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    HK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
+
+}  // namespace
+
+// ==================================================================================================
+HK_EXPORT int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx** out) {
+    if (!out) return HK_ERR_INVALID;
+    *out = nullptr;
+    if (curve != HK_CURVE_BLS12_381 && curve != HK_CURVE_BN254) return HK_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return HK_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return HK_ERR_NO_DEVICE;
+    if (prop.major != 10) return HK_ERR_NO_DEVICE;   // built for sm_100a only; no fallback
+    hk_ctx* ctx = new (std::nothrow) hk_ctx();
+    if (!ctx) return HK_ERR_NOMEM;
+    ctx->device = device;
+    ctx->curve = curve;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return HK_ERR_CUDA;
+    }
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return HK_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    *out = ctx;
+    return HK_OK;
+}
+
+HK_EXPORT int32_t hk_ctx_destroy(hk_ctx* ctx) {
+    if (!ctx) return HK_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->pks.clear();
+    ctx->r1cs.clear();
+    ctx->domains.clear();
+    ctx->bases.clear();
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return HK_OK;
+}
+
+HK_EXPORT int32_t hk_ctx_sync(hk_ctx* ctx) {
+    return guarded(ctx, [&] { HK_CUDA(cudaStreamSynchronize(ctx->stream)); });
+}
+
+HK_EXPORT const char* hk_last_error_string(hk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+HK_EXPORT int32_t hk_curve_info(hk_ctx* ctx, uint32_t* fq_limbs64, uint32_t* fr_limbs64, uint32_t* fr_bits,
+                                uint32_t* two_adicity) {
+    if (!ctx) return HK_ERR_INVALID;
+    bool bls = ctx->curve == HK_CURVE_BLS12_381;
+    if (fq_limbs64) *fq_limbs64 = bls ? 6 : 4;
+    if (fr_limbs64) *fr_limbs64 = 4;
+    if (fr_bits) *fr_bits = bls ? 255 : 254;
+    if (two_adicity) *two_adicity = bls ? 32 : 28;
+    return HK_OK;
+}
+
+HK_EXPORT uint64_t hk_launch_count(hk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+HK_EXPORT int32_t hk_bases_upload_g1(hk_ctx* ctx, const void* p, const uint8_t* inf, size_t n, uint32_t memspace,
+                                     uint64_t* handle) {
+    return guarded(ctx, [&] { bases_upload(ctx, 1, p, inf, n, memspace, handle); });
+}
+HK_EXPORT int32_t hk_bases_upload_g2(hk_ctx* ctx, const void* p, const uint8_t* inf, size_t n, uint32_t memspace,
+                                     uint64_t* handle) {
+    return guarded(ctx, [&] { bases_upload(ctx, 2, p, inf, n, memspace, handle); });
+}
+HK_EXPORT int32_t hk_bases_free(hk_ctx* ctx, uint64_t handle) {
+    return guarded(ctx, [&] {
+        auto it = ctx->bases.find(handle);
+        HK_REQUIRE(it != ctx->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->bases.erase(it);
+    });
+}
+HK_EXPORT int32_t hk_bases_len(hk_ctx* ctx, uint64_t handle, size_t* n) {
+    return guarded(ctx, [&] {
+        auto it = ctx->bases.find(handle);
+        HK_REQUIRE(it != ctx->bases.end() && n, HK_ERR_HANDLE, "unknown base-set handle");
+        *n = it->second->n;
+    });
+}
+HK_EXPORT int32_t hk_bases_download(hk_ctx* ctx, uint64_t handle, size_t offset, size_t n, void* out) {
+    return guarded(ctx, [&] {
+        auto it = ctx->bases.find(handle);
+        HK_REQUIRE(it != ctx->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
+        BaseSet& bs = *it->second;
+        HK_REQUIRE(out && offset + n <= bs.n, HK_ERR_INVALID, "range outside the base set");
+        if (n == 0) return;
+        HK_CUDA(cudaMemcpyAsync(out, (char*)bs.d + offset * bs.point_bytes, n * bs.point_bytes, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+HK_EXPORT int32_t hk_bases_from_scalars_g1(hk_ctx* ctx, const void* gen, const uint64_t* scalars, size_t n,
+                                           uint32_t repr, uint32_t memspace, uint64_t* handle) {
+    return guarded(ctx, [&] { bases_from_scalars(ctx, 1, gen, scalars, n, repr, memspace, handle); });
+}
+HK_EXPORT int32_t hk_bases_from_scalars_g2(hk_ctx* ctx, const void* gen, const uint64_t* scalars, size_t n,
+                                           uint32_t repr, uint32_t memspace, uint64_t* handle) {
+    return guarded(ctx, [&] { bases_from_scalars(ctx, 2, gen, scalars, n, repr, memspace, handle); });
+}
+
+HK_EXPORT int32_t hk_msm_g1(hk_ctx* ctx, uint64_t bases, size_t off, const uint64_t* sc, size_t n, uint32_t repr,
+                            uint32_t memspace, void* out) {
+    return guarded(ctx, [&] { msm_entry(ctx, 1, bases, off, sc, n, 1, repr, memspace, out); });
+}
+HK_EXPORT int32_t hk_msm_g2(hk_ctx* ctx, uint64_t bases, size_t off, const uint64_t* sc, size_t n, uint32_t repr,
+                            uint32_t memspace, void* out) {
+    return guarded(ctx, [&] { msm_entry(ctx, 2, bases, off, sc, n, 1, repr, memspace, out); });
+}
+HK_EXPORT int32_t hk_msm_g1_checked(hk_ctx* ctx, uint64_t bases, size_t off, size_t n_bases_expected,
+                                    const uint64_t* sc, size_t n, uint32_t repr, uint32_t memspace, void* out) {
+    return guarded(ctx, [&] {
+        // VariableBaseMSM::msm: Err(min_len) when bases.len() != scalars.len()
+        HK_REQUIRE(n_bases_expected == n, HK_ERR_LENGTH,
+                   "msm: bases and scalars differ in length (min = " +
+                       std::to_string(n_bases_expected < n ? n_bases_expected : n) + ")");
+        BaseSet& bs = find_bases(ctx, bases, 1);
+        HK_REQUIRE(off + n <= bs.n, HK_ERR_LENGTH, "msm: base range outside the base set");
+        msm_entry(ctx, 1, bases, off, sc, n, 1, repr, memspace, out);
+    });
+}
+HK_EXPORT int32_t hk_msm_g1_batch(hk_ctx* ctx, uint64_t bases, size_t off, const uint64_t* sc, size_t n, size_t K,
+                                  uint32_t repr, uint32_t memspace, void* out) {
+    return guarded(ctx, [&] { msm_entry(ctx, 1, bases, off, sc, n, K, repr, memspace, out); });
+}
+HK_EXPORT int32_t hk_msm_g2_batch(hk_ctx* ctx, uint64_t bases, size_t off, const uint64_t* sc, size_t n, size_t K,
+                                  uint32_t repr, uint32_t memspace, void* out) {
+    return guarded(ctx, [&] { msm_entry(ctx, 2, bases, off, sc, n, K, repr, memspace, out); });
+}
+
+HK_EXPORT int32_t hk_g1_into_affine(hk_ctx* ctx, const void* jac, size_t n, void* out_xy, uint8_t* inf_out) {
+    return guarded(ctx, [&] { into_affine_entry(ctx, 1, jac, n, out_xy, inf_out); });
+}
+HK_EXPORT int32_t hk_g2_into_affine(hk_ctx* ctx, const void* jac, size_t n, void* out_xy, uint8_t* inf_out) {
+    return guarded(ctx, [&] { into_affine_entry(ctx, 2, jac, n, out_xy, inf_out); });
+}
+
+HK_EXPORT int32_t hk_ntt_batch(hk_ctx* ctx, uint64_t* inout, uint32_t log_n, size_t K, uint32_t dir, uint32_t domain,
+                               uint32_t memspace) {
+    return guarded(ctx, [&] {
+        HK_REQUIRE(inout || K == 0, HK_ERR_INVALID, "inout is NULL");
+        HK_REQUIRE(dir == HK_NTT_FORWARD || dir == HK_NTT_INVERSE, HK_ERR_INVALID, "bad dir");
+        HK_REQUIRE(domain == HK_DOMAIN_PLAIN || domain == HK_DOMAIN_COSET_GENERATOR, HK_ERR_INVALID, "bad domain");
+        uint32_t adic = ctx->curve == HK_CURVE_BLS12_381 ? 32 : 28;
+        HK_REQUIRE(log_n <= adic, HK_ERR_UNSUPPORTED, "ntt: log_n exceeds the two-adicity of Fr");
+        if (K == 0) return;
+        size_t bytes = (K << log_n) * 32;
+        uint64_t* d = inout;
+        if (memspace != HK_DEVICE) {
+            d = ctx->ws_io[0].as<uint64_t>(bytes / 8);
+            HK_CUDA(cudaMemcpyAsync(d, inout, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        by_curve(ctx, [&] { ntt_run<Bls12381>(ctx, d, log_n, K, dir, domain); },
+                 [&] { ntt_run<Bn254>(ctx, d, log_n, K, dir, domain); });
+        if (memspace != HK_DEVICE) {
+            HK_CUDA(cudaMemcpyAsync(inout, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    });
+}
+HK_EXPORT int32_t hk_ntt(hk_ctx* ctx, uint64_t* inout, uint32_t log_n, uint32_t dir, uint32_t domain, uint32_t memspace) {
+    return hk_ntt_batch(ctx, inout, log_n, 1, dir, domain, memspace);
+}
+
+HK_EXPORT int32_t hk_qap_h(hk_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint32_t log_n,
+                           uint32_t memspace, uint64_t* h) {
+    return guarded(ctx, [&] {
+        HK_REQUIRE(a && b && c && h, HK_ERR_INVALID, "NULL argument");
+        uint32_t adic = ctx->curve == HK_CURVE_BLS12_381 ? 32 : 28;
+        HK_REQUIRE(log_n >= 1 && log_n <= adic, HK_ERR_UNSUPPORTED, "qap_h: log_n out of range");
+        const size_t N = size_t(1) << log_n;
+        uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N);
+        cudaMemcpyKind kind = memspace == HK_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        HK_CUDA(cudaMemcpyAsync(abc, a, N * 32, kind, ctx->stream));
+        HK_CUDA(cudaMemcpyAsync(abc + 4 * N, b, N * 32, kind, ctx->stream));
+        HK_CUDA(cudaMemcpyAsync(abc + 8 * N, c, N * 32, kind, ctx->stream));
+        uint64_t* dh = memspace == HK_DEVICE ? h : ctx->ws_qap[1].as<uint64_t>(4 * N);
+        by_curve(ctx, [&] { qap_h_from_evals<Bls12381>(ctx, log_n, abc, dh); },
+                 [&] { qap_h_from_evals<Bn254>(ctx, log_n, abc, dh); });
+        if (memspace != HK_DEVICE) {
+            HK_CUDA(cudaMemcpyAsync(h, dh, N * 32, cudaMemcpyDeviceToHost, ctx->stream));
+            HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    });
+}
+
+HK_EXPORT int32_t hk_r1cs_upload(hk_ctx* ctx, size_t n, size_t l, size_t nw, const uint32_t* a_ptr,
+                                 const uint32_t* a_col, const uint64_t* a_val, const uint32_t* b_ptr,
+                                 const uint32_t* b_col, const uint64_t* b_val, const uint32_t* c_ptr,
+                                 const uint32_t* c_col, const uint64_t* c_val, uint64_t* handle) {
+    return guarded(ctx, [&] {
+        HK_REQUIRE(handle && a_ptr && b_ptr && c_ptr, HK_ERR_INVALID, "NULL argument");
+        const uint32_t* ptr[3] = {a_ptr, b_ptr, c_ptr};
+        const uint32_t* col[3] = {a_col, b_col, c_col};
+        const uint64_t* val[3] = {a_val, b_val, c_val};
+        auto m = r1cs_upload(ctx, n, l, nw, ptr, col, val);
+        uint32_t adic = ctx->curve == HK_CURVE_BLS12_381 ? 32 : 28;
+        HK_REQUIRE(m->log_n <= adic, HK_ERR_UNSUPPORTED, "r1cs: domain larger than 2^two_adicity");
+        uint64_t h = new_handle(ctx);
+        ctx->r1cs[h] = m;
+        *handle = h;
+    });
+}
+HK_EXPORT int32_t hk_r1cs_free(hk_ctx* ctx, uint64_t handle) {
+    return guarded(ctx, [&] {
+        auto it = ctx->r1cs.find(handle);
+        HK_REQUIRE(it != ctx->r1cs.end(), HK_ERR_HANDLE, "unknown r1cs handle");
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->r1cs.erase(it);
+    });
+}
+HK_EXPORT int32_t hk_qap_witness_map(hk_ctx* ctx, uint64_t r1cs, const uint64_t* z, uint32_t memspace, uint64_t* h) {
+    return guarded(ctx, [&] {
+        auto it = ctx->r1cs.find(r1cs);
+        HK_REQUIRE(it != ctx->r1cs.end(), HK_ERR_HANDLE, "unknown r1cs handle");
+        HK_REQUIRE(z && h, HK_ERR_INVALID, "NULL argument");
+        R1csDev& m = *it->second;
+        const size_t N = size_t(1) << m.log_n;
+        const uint64_t* dz = (const uint64_t*)to_device(ctx, ctx->ws_z, z, (m.l + m.nw) * 32, memspace);
+        uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N);
+        uint64_t* dh = memspace == HK_DEVICE ? h : ctx->ws_qap[1].as<uint64_t>(4 * N);
+        by_curve(ctx,
+                 [&] {
+                     r1cs_evals<Bls12381>(ctx, m, dz, abc);
+                     qap_h_from_evals<Bls12381>(ctx, m.log_n, abc, dh);
+                 },
+                 [&] {
+                     r1cs_evals<Bn254>(ctx, m, dz, abc);
+                     qap_h_from_evals<Bn254>(ctx, m.log_n, abc, dh);
+                 });
+        if (memspace != HK_DEVICE) {
+            HK_CUDA(cudaMemcpyAsync(h, dh, N * 32, cudaMemcpyDeviceToHost, ctx->stream));
+            HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    });
+}
+
+HK_EXPORT int32_t hk_pk_create(hk_ctx* ctx, const hk_pk_desc* desc, uint64_t* pk_handle) {
+    return guarded(ctx, [&] {
+        HK_REQUIRE(desc && pk_handle, HK_ERR_INVALID, "NULL argument");
+        HK_REQUIRE(desc->alpha_g && desc->beta_g && desc->beta_h && desc->last_delta_h, HK_ERR_INVALID,
+                   "pk: vk points missing");
+        std::shared_ptr<PkDev> pk;
+        by_curve(ctx, [&] { pk = pk_create<Bls12381>(ctx, *desc); }, [&] { pk = pk_create<Bn254>(ctx, *desc); });
+        uint64_t h = new_handle(ctx);
+        ctx->pks[h] = pk;
+        *pk_handle = h;
+    });
+}
+HK_EXPORT int32_t hk_pk_free(hk_ctx* ctx, uint64_t pk_handle) {
+    return guarded(ctx, [&] {
+        auto it = ctx->pks.find(pk_handle);
+        HK_REQUIRE(it != ctx->pks.end(), HK_ERR_HANDLE, "unknown pk handle");
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->pks.erase(it);
+    });
+}
+
+HK_EXPORT int32_t hk_commit(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, const uint64_t* z, const uint64_t* kappa,
+                            uint32_t memspace, void* com_affine, uint8_t* com_inf) {
+    return guarded(ctx, [&] {
+        auto it = ctx->pks.find(pk_h);
+        HK_REQUIRE(it != ctx->pks.end(), HK_ERR_HANDLE, "unknown pk handle");
+        HK_REQUIRE(z && kappa && com_affine, HK_ERR_INVALID, "NULL argument");
+        PkDev& pk = *it->second;
+        HK_REQUIRE(stage < pk.num_stages, HK_ERR_INVALID, "commit: no such stage");
+        const size_t need = pk.r1cs->l + pk.stage_start[stage + 1];
+        const uint64_t* dz = (const uint64_t*)to_device(ctx, ctx->ws_z, z, need * 32, memspace);
+        const uint64_t* dk = (const uint64_t*)to_device(ctx, ctx->ws_io[2], kappa, 32, memspace);
+        const size_t pb = point_bytes(ctx, 1);
+        char* d_out = memspace == HK_DEVICE ? (char*)com_affine : (char*)ctx->ws_io[3].ensure(pb + 64);
+        uint8_t* d_inf = memspace == HK_DEVICE ? com_inf : (uint8_t*)(d_out + pb);
+        by_curve(ctx, [&] { commit_run<Bls12381>(ctx, pk, stage, dz, dk, d_out, d_inf); },
+                 [&] { commit_run<Bn254>(ctx, pk, stage, dz, dk, d_out, d_inf); });
+        if (memspace != HK_DEVICE) {
+            HK_CUDA(cudaMemcpyAsync(com_affine, d_out, pb, cudaMemcpyDeviceToHost, ctx->stream));
+            if (com_inf) HK_CUDA(cudaMemcpyAsync(com_inf, d_inf, 1, cudaMemcpyDeviceToHost, ctx->stream));
+            HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    });
+}
+
+HK_EXPORT int32_t hk_prove(hk_ctx* ctx, uint64_t pk_h, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                           const uint64_t* kappas, uint32_t memspace, void* a_affine, void* b_affine, void* c_affine,
+                           uint8_t* inf) {
+    return guarded(ctx, [&] {
+        auto it = ctx->pks.find(pk_h);
+        HK_REQUIRE(it != ctx->pks.end(), HK_ERR_HANDLE, "unknown pk handle");
+        PkDev& pk = *it->second;
+        HK_REQUIRE(z && r && s && a_affine && b_affine && c_affine, HK_ERR_INVALID, "NULL argument");
+        HK_REQUIRE(kappas || pk.num_stages == 1, HK_ERR_INVALID, "kappas is NULL");
+        const size_t p1 = point_bytes(ctx, 1), p2 = point_bytes(ctx, 2);
+        const uint32_t nk = pk.num_stages - 1;
+        if (memspace == HK_DEVICE) {
+            by_curve(ctx, [&] { prove_run<Bls12381>(ctx, pk, z, r, s, kappas, a_affine, b_affine, c_affine, inf); },
+                     [&] { prove_run<Bn254>(ctx, pk, z, r, s, kappas, a_affine, b_affine, c_affine, inf); });
+            return;
+        }
+        // host staging: z | r | s | kappas in one pinned buffer, one H2D copy
+        const size_t zb = pk.m * 32;
+        const size_t total = zb + 64 + (size_t)nk * 32;
+        char* pin = (char*)ctx->pinned_buf(total + 2 * p1 + p2 + 16);
+        memcpy(pin, z, zb);
+        memcpy(pin + zb, r, 32);
+        memcpy(pin + zb + 32, s, 32);
+        if (nk) memcpy(pin + zb + 64, kappas, (size_t)nk * 32);
+        char* dz = (char*)ctx->ws_z.ensure(total + 64);
+        HK_CUDA(cudaMemcpyAsync(dz, pin, total, cudaMemcpyHostToDevice, ctx->stream));
+        char* d_out = (char*)ctx->ws_io[3].ensure(2 * p1 + p2 + 64);
+        uint8_t* d_inf = (uint8_t*)(d_out + 2 * p1 + p2);
+        const uint64_t* dzz = (const uint64_t*)dz;
+        const uint64_t* dr = (const uint64_t*)(dz + zb);
+        const uint64_t* ds = (const uint64_t*)(dz + zb + 32);
+        const uint64_t* dk = (const uint64_t*)(dz + zb + 64);
+        by_curve(ctx, [&] { prove_run<Bls12381>(ctx, pk, dzz, dr, ds, dk, d_out, d_out + p1, d_out + p1 + p2, d_inf); },
+                 [&] { prove_run<Bn254>(ctx, pk, dzz, dr, ds, dk, d_out, d_out + p1, d_out + p1 + p2, d_inf); });
+        char* pout = pin + total;
+        HK_CUDA(cudaMemcpyAsync(pout, d_out, 2 * p1 + p2 + 3, cudaMemcpyDeviceToHost, ctx->stream));
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(a_affine, pout, p1);
+        memcpy(b_affine, pout + p1, p2);
+        memcpy(c_affine, pout + p1 + p2, p1);
+        if (inf) memcpy(inf, pout + 2 * p1 + p2, 3);
+    });
+}
+
+HK_EXPORT int32_t hk_field_op(hk_ctx* ctx, uint32_t field, uint32_t op, const uint64_t* a, const uint64_t* b,
+                              uint64_t* out, size_t n) {
+    return guarded(ctx, [&] {
+        HK_REQUIRE(a && out, HK_ERR_INVALID, "NULL argument");
+        HK_REQUIRE(op <= HK_FOP_FROM_MONT, HK_ERR_INVALID, "bad op");
+        HK_REQUIRE(b || op >= HK_FOP_INV, HK_ERR_INVALID, "b is NULL");
+        if (n == 0) return;
+        bool bls = ctx->curve == HK_CURVE_BLS12_381;
+        if (field == HK_FIELD_FR) {
+            if (bls) field_op_run<Bls12381::Fr>(ctx, op, a, b, out, n);
+            else field_op_run<Bn254::Fr>(ctx, op, a, b, out, n);
+        } else if (field == HK_FIELD_FQ) {
+            if (bls) field_op_run<Bls12381::Fq>(ctx, op, a, b, out, n);
+            else field_op_run<Bn254::Fq>(ctx, op, a, b, out, n);
+        } else if (field == HK_FIELD_FQ2) {
+            if (bls) field_op_run<Bls12381::Fq2>(ctx, op, a, b, out, n);
+            else field_op_run<Bn254::Fq2>(ctx, op, a, b, out, n);
+        } else {
+            throw HkError{HK_ERR_INVALID, "bad field id"};
+        }
+    });
+}
+
+HK_EXPORT int32_t hk_bench_field_mul(hk_ctx* ctx, uint32_t field, uint32_t threads, uint32_t iters, float* ms) {
+    return guarded(ctx, [&] {
+        HK_REQUIRE(ms && threads && iters, HK_ERR_INVALID, "bad argument");
+        bool bls = ctx->curve == HK_CURVE_BLS12_381;
+        threads = (threads + 255) / 256 * 256;
+        void* out = ctx->ws_io[0].ensure((size_t)threads * 48);
+        auto run = [&](auto tag) {
+            using F = decltype(tag);
+            k_bench_mul<F><<<threads / 256, 256, 0, ctx->stream>>>((F*)out, 2);   // warm-up
+            *ms = time_ms(ctx, [&] {
+                k_bench_mul<F><<<threads / 256, 256, 0, ctx->stream>>>((F*)out, iters);
+                ctx->launches++;
+            });
+            HK_CUDA(cudaGetLastError());
+        };
+        if (field == HK_FIELD_FR) {
+            if (bls) run(Bls12381::Fr{});
+            else run(Bn254::Fr{});
+        } else if (field == HK_FIELD_FQ) {
+            if (bls) run(Bls12381::Fq{});
+            else run(Bn254::Fq{});
+        } else {
+            throw HkError{HK_ERR_INVALID, "bench: field must be FR or FQ"};
+        }
+    });
+}
+
+HK_EXPORT int32_t hk_bench_imad_wide(hk_ctx* ctx, uint32_t iters, double* macs_per_s) {
+    return guarded(ctx, [&] {
+        HK_REQUIRE(macs_per_s && iters, HK_ERR_INVALID, "bad argument");
+        const uint32_t blocks = ctx->sm_count * 8, tpb = 256;
+        uint64_t* out = ctx->ws_io[0].as<uint64_t>((size_t)blocks * tpb);
+        k_bench_imad_wide<<<blocks, tpb, 0, ctx->stream>>>(out, 4);
+        float ms = time_ms(ctx, [&] {
+            k_bench_imad_wide<<<blocks, tpb, 0, ctx->stream>>>(out, iters);
+            ctx->launches++;
+        });
+        HK_CUDA(cudaGetLastError());
+        double macs = (double)blocks * tpb * (double)iters * 32.0;
+        *macs_per_s = macs / (ms * 1e-3);
+    });
+}

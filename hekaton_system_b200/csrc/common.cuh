@@ -1,0 +1,203 @@
+// Context, error handling, workspace management shared by every translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/hekaton_b200.h"
+#include "ec.cuh"
+
+namespace hk {
+
+// ---------------------------------------------------------------------------------------
+// curve configurations
+// ---------------------------------------------------------------------------------------
+struct Bls12381 {
+    using Fq = Fp<bls12_381_fq_tag>;
+    using Fr = Fp<bls12_381_fr_tag>;
+    using Fq2 = Fp2T<Fq>;
+    static constexpr uint32_t ID = HK_CURVE_BLS12_381;
+    static constexpr int FR_BITS = 255;
+    static constexpr int TWO_ADICITY = 32;
+    static constexpr uint64_t FR_GENERATOR = 7;
+};
+struct Bn254 {
+    using Fq = Fp<bn254_fq_tag>;
+    using Fr = Fp<bn254_fr_tag>;
+    using Fq2 = Fp2T<Fq>;
+    static constexpr uint32_t ID = HK_CURVE_BN254;
+    static constexpr int FR_BITS = 254;
+    static constexpr int TWO_ADICITY = 28;
+    static constexpr uint64_t FR_GENERATOR = 5;
+};
+
+struct Scalar256 {
+    uint64_t v[4];
+};
+
+// coordinate field of G1 / G2
+template <class Curve, int GROUP>
+struct GroupFieldT;
+template <class Curve>
+struct GroupFieldT<Curve, 1> {
+    using F = typename Curve::Fq;
+};
+template <class Curve>
+struct GroupFieldT<Curve, 2> {
+    using F = typename Curve::Fq2;
+};
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+struct HkError {
+    int32_t code;
+    std::string msg;
+};
+
+#define HK_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            throw hk::HkError{HK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + \
+                                               " (" __FILE__ ":" + std::to_string(__LINE__) + ")"}; \
+        }                                                                                      \
+    } while (0)
+
+#define HK_REQUIRE(cond, code, text)                    \
+    do {                                                \
+        if (!(cond)) throw hk::HkError{(code), (text)}; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// grow-only device buffer
+// ---------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    void* ensure(size_t bytes) {
+        if (bytes > cap) {
+            if (p) {
+                cudaFree(p);
+                p = nullptr;
+                cap = 0;
+            }
+            size_t want = bytes + bytes / 8 + 256;
+            cudaError_t e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) {
+                p = nullptr;
+                throw HkError{HK_ERR_NOMEM, std::string("cudaMalloc(") + std::to_string(want) + "): " +
+                                                cudaGetErrorString(e)};
+            }
+            cap = want;
+        }
+        return p;
+    }
+    template <class T>
+    T* as(size_t count) {
+        return reinterpret_cast<T*>(ensure(count * sizeof(T)));
+    }
+};
+
+struct BaseSet {
+    int group = 1;          // 1 = G1, 2 = G2
+    size_t n = 0;
+    size_t point_bytes = 0;
+    void* d = nullptr;      // affine points, AoS
+    ~BaseSet() {
+        if (d) cudaFree(d);
+    }
+};
+
+struct NttDomain;   // ntt.cu
+struct R1csDev;     // qap.cu
+struct PkDev;       // prove.cu
+
+}  // namespace hk
+
+struct hk_ctx {
+    int device = 0;
+    uint32_t curve = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    uint64_t launches = 0;
+    uint64_t next_handle = 1;
+    int sm_count = 148;
+
+    std::map<uint64_t, std::unique_ptr<hk::BaseSet>> bases;
+    std::map<uint32_t, std::shared_ptr<hk::NttDomain>> domains;   // by log_n
+    std::map<uint64_t, std::shared_ptr<hk::R1csDev>> r1cs;
+    std::map<uint64_t, std::shared_ptr<hk::PkDev>> pks;
+
+    // scratch (grow-only; a context is single-threaded by contract)
+    hk::DevBuf ws_scalars, ws_hist, ws_items, ws_buckets, ws_chunks, ws_wsum, ws_out, ws_scan;
+    hk::DevBuf ws_ntt_tmp, ws_qap[4], ws_io[4], ws_z, ws_misc;
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+
+    void* pinned_buf(size_t bytes) {
+        if (bytes > pinned_cap) {
+            if (pinned) cudaFreeHost(pinned);
+            pinned = nullptr;
+            pinned_cap = 0;
+            if (cudaMallocHost(&pinned, bytes + 256) != cudaSuccess)
+                throw hk::HkError{HK_ERR_NOMEM, "cudaMallocHost failed"};
+            pinned_cap = bytes + 256;
+        }
+        return pinned;
+    }
+};
+
+namespace hk {
+
+inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Wraps every extern "C" body: activates the device, maps exceptions to codes.
+template <class Fn>
+inline int32_t guarded(hk_ctx* ctx, Fn&& fn) {
+    if (!ctx) return HK_ERR_INVALID;
+    try {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) throw HkError{HK_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
+        fn();
+        return HK_OK;
+    } catch (const HkError& e) {
+        ctx->err = e.msg;
+        return e.code;
+    } catch (const std::exception& e) {
+        ctx->err = e.what();
+        return HK_ERR_INVALID;
+    } catch (...) {
+        ctx->err = "unknown exception";
+        return HK_ERR_INVALID;
+    }
+}
+
+#define HK_LAUNCH_CHECK(ctx)       \
+    do {                           \
+        (ctx)->launches++;         \
+        HK_CUDA(cudaGetLastError()); \
+    } while (0)
+
+// ---- per-module entry points (implemented in the respective .cu files) -----------------
+// msm: bases/scalars are device pointers; out_xyzz receives K XYZZ points (device).
+template <class Curve, int GROUP>
+void msm_run(hk_ctx* ctx, const void* d_bases, size_t n, const Scalar256* d_scalars, size_t K, bool scalars_mont,
+             void* d_out_jac);
+
+template <class Curve>
+void ntt_run(hk_ctx* ctx, uint64_t* d_data, uint32_t log_n, size_t K, uint32_t dir, uint32_t domain);
+
+}  // namespace hk

@@ -1,0 +1,147 @@
+// Field wrappers over the generated Montgomery kernels (field_gen.cuh).
+//
+// Values are kept in Montgomery form, little-endian 64-bit lanes -- the same memory
+// layout as ark-ff 0.4 `Fp<MontBackend<_, N>, N>` (`BigInt<N>([u64; N])`), which is what
+// crosses the drop-in boundary.  Device only.
+#pragma once
+#include <cstdint>
+#include "field_gen.cuh"
+
+namespace hk {
+
+// Tag types binding a generated field to the template below.
+#define HK_DEFINE_FIELD_TAG(NAME)                                                             \
+    struct NAME##_tag {                                                                       \
+        using raw_t = NAME##_t;                                                               \
+        using params = NAME##_params;                                                         \
+        static constexpr int N64 = NAME##_params::N64;                                        \
+        static constexpr int BITS = NAME##_params::BITS;                                      \
+        __device__ __forceinline__ static void mul(raw_t& r, const raw_t& a, const raw_t& b) { NAME##_mul(r, a, b); } \
+        __device__ __forceinline__ static void add(raw_t& r, const raw_t& a, const raw_t& b) { NAME##_add(r, a, b); } \
+        __device__ __forceinline__ static void sub(raw_t& r, const raw_t& a, const raw_t& b) { NAME##_sub(r, a, b); } \
+        __device__ __forceinline__ static uint64_t mod(int i) { return NAME##_MOD[i]; }       \
+        __device__ __forceinline__ static uint64_t one(int i) { return NAME##_ONE[i]; }       \
+        __device__ __forceinline__ static uint64_t r2(int i) { return NAME##_R2[i]; }         \
+    };
+
+HK_DEFINE_FIELD_TAG(bls12_381_fq)
+HK_DEFINE_FIELD_TAG(bls12_381_fr)
+HK_DEFINE_FIELD_TAG(bn254_fq)
+HK_DEFINE_FIELD_TAG(bn254_fr)
+
+template <class Tag>
+struct Fp {
+    using raw_t = typename Tag::raw_t;
+    static constexpr int N64 = Tag::N64;
+    static constexpr int BITS = Tag::BITS;
+    raw_t r;
+
+    __device__ __forceinline__ static Fp zero() {
+        Fp z;
+#pragma unroll
+        for (int i = 0; i < N64; i++) z.r.v[i] = 0;
+        return z;
+    }
+    __device__ __forceinline__ static Fp one() {
+        Fp z;
+#pragma unroll
+        for (int i = 0; i < N64; i++) z.r.v[i] = Tag::one(i);
+        return z;
+    }
+    __device__ __forceinline__ bool is_zero() const {
+        uint64_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N64; i++) o |= r.v[i];
+        return o == 0;
+    }
+    __device__ __forceinline__ bool operator==(const Fp& b) const {
+        uint64_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N64; i++) o |= (r.v[i] ^ b.r.v[i]);
+        return o == 0;
+    }
+    __device__ __forceinline__ bool operator!=(const Fp& b) const { return !(*this == b); }
+
+    __device__ __forceinline__ Fp operator*(const Fp& b) const { Fp o; Tag::mul(o.r, r, b.r); return o; }
+    __device__ __forceinline__ Fp operator+(const Fp& b) const { Fp o; Tag::add(o.r, r, b.r); return o; }
+    __device__ __forceinline__ Fp operator-(const Fp& b) const { Fp o; Tag::sub(o.r, r, b.r); return o; }
+    __device__ __forceinline__ Fp sqr() const { Fp o; Tag::mul(o.r, r, r); return o; }
+    __device__ __forceinline__ Fp dbl() const { Fp o; Tag::add(o.r, r, r); return o; }
+    __device__ __forceinline__ Fp neg() const { Fp z = zero(); Fp o; Tag::sub(o.r, z.r, r); return o; }
+
+    // Montgomery <-> canonical
+    __device__ __forceinline__ Fp from_mont() const {
+        Fp u = zero();
+        u.r.v[0] = 1;
+        return (*this) * u;
+    }
+    __device__ __forceinline__ Fp to_mont() const {
+        Fp rr;
+#pragma unroll
+        for (int i = 0; i < N64; i++) rr.r.v[i] = Tag::r2(i);
+        return (*this) * rr;
+    }
+
+    // a^(p-2); not constant time (nothing here is secret-dependent in a way that matters
+    // for a prover's public outputs).  0 -> 0.
+    __device__ __noinline__ Fp inverse() const {
+        // exponent p - 2, scanned MSB -> LSB
+        uint64_t e[N64];
+#pragma unroll
+        for (int i = 0; i < N64; i++) e[i] = Tag::mod(i);
+        e[0] -= 2;  // p is odd and > 2: no borrow
+        Fp acc = one();
+        bool started = false;
+        for (int i = BITS - 1; i >= 0; i--) {
+            if (started) acc = acc.sqr();
+            if ((e[i >> 6] >> (i & 63)) & 1) {
+                acc = started ? acc * (*this) : (*this);
+                started = true;
+            }
+        }
+        return acc;
+    }
+
+    // small-integer constant in Montgomery form (k * R mod p) by repeated addition
+    __device__ __forceinline__ static Fp from_small(unsigned k) {
+        Fp acc = zero(), o = one();
+        for (unsigned i = 0; i < k; i++) acc = acc + o;
+        return acc;
+    }
+};
+
+// Fq2 = Fq[u]/(u^2 + 1) (both BLS12-381 and BN254 use the non-residue -1).
+template <class F>
+struct Fp2T {
+    using base = F;
+    F c0, c1;
+    __device__ __forceinline__ static Fp2T zero() { return {F::zero(), F::zero()}; }
+    __device__ __forceinline__ static Fp2T one() { return {F::one(), F::zero()}; }
+    __device__ __forceinline__ bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    __device__ __forceinline__ bool operator==(const Fp2T& b) const { return c0 == b.c0 && c1 == b.c1; }
+    __device__ __forceinline__ bool operator!=(const Fp2T& b) const { return !(*this == b); }
+    __device__ __forceinline__ Fp2T operator+(const Fp2T& b) const { return {c0 + b.c0, c1 + b.c1}; }
+    __device__ __forceinline__ Fp2T operator-(const Fp2T& b) const { return {c0 - b.c0, c1 - b.c1}; }
+    __device__ __forceinline__ Fp2T dbl() const { return {c0.dbl(), c1.dbl()}; }
+    __device__ __forceinline__ Fp2T neg() const { return {c0.neg(), c1.neg()}; }
+    __device__ __forceinline__ Fp2T operator*(const Fp2T& b) const {
+        F t0 = c0 * b.c0;
+        F t1 = c1 * b.c1;
+        F s = (c0 + c1) * (b.c0 + b.c1);
+        return {t0 - t1, s - t0 - t1};
+    }
+    __device__ __forceinline__ Fp2T sqr() const {
+        F s = c0 + c1;
+        F d = c0 - c1;
+        F m = c0 * c1;
+        return {s * d, m.dbl()};
+    }
+    __device__ __forceinline__ Fp2T inverse() const {
+        F n = (c0.sqr() + c1.sqr()).inverse();
+        return {c0 * n, (c1 * n).neg()};
+    }
+    __device__ __forceinline__ Fp2T from_mont() const { return {c0.from_mont(), c1.from_mont()}; }
+    __device__ __forceinline__ Fp2T to_mont() const { return {c0.to_mont(), c1.to_mont()}; }
+};
+
+}  // namespace hk

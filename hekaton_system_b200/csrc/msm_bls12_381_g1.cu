@@ -1,0 +1,5 @@
+// Explicit instantiation of the MSM pipeline for Bls12381 G1 (one TU per group keeps builds parallel).
+#include "msm_impl.cuh"
+namespace hk {
+template void msm_run<Bls12381, 1>(hk_ctx*, const void*, size_t, const Scalar256*, size_t, bool, void*);
+}

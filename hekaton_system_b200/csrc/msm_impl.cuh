@@ -1,0 +1,440 @@
+// Pippenger MSM for sm_100a.  Replaces ark-ec 0.4 `VariableBaseMSM::msm_bigint` as called from
+// /root/reference/cp-groth16/src/prover.rs:117,129,168 and committer.rs:89,113.
+//
+// Pipeline (all on the context stream, no host synchronisation):
+//   1. k_msm_hist      signed-digit recoding of every scalar (window c, digits in
+//                      [-2^(c-1), 2^(c-1)], top window unrecoded) + histogram of
+//                      (window, |digit|) keys
+//   2. exclusive scan  bucket start offsets
+//   3. k_msm_scatter   counting sort: item = (point index << 1 | sign) placed in its bucket run
+//   4. k_msm_accum     balanced segmented accumulation: every thread owns a fixed-length
+//                      segment of the sorted item list (so skewed 0/1-heavy witness scalars
+//                      cost the same as uniform ones), interior runs go straight to their
+//                      bucket, the two boundary runs of each segment go to a partial list
+//                      that is folded by k_msm_fold (recursively, same scheme)
+//   5. k_msm_reduce*   per window sum_b b*B_b by chunked running sums, tree sum per window
+//   6. k_msm_combine   Horner over windows -> one Jacobian point
+#pragma once
+#include "common.cuh"
+
+namespace hk {
+
+struct MsmPlan {
+    int c;       // window bits
+    int W;       // windows
+    uint32_t B;  // buckets per window = 2^(c-1)
+};
+
+inline MsmPlan msm_plan(size_t n, int scalar_bits, int group) {
+    // cost model in field multiplications: accumulate 10/pt/window, reduce ~ (2*14 + tail) per bucket
+    double best = 1e300;
+    MsmPlan p{4, 0, 0};
+    for (int c = 3; c <= 16; c++) {
+        int W = (scalar_bits + 1 + c - 1) / c;
+        double B = double(1u << (c - 1));
+        double cost = W * (double(n) * 10.0 + B * 45.0);
+        if (cost < best) {
+            best = cost;
+            p = {c, W, 1u << (c - 1)};
+        }
+    }
+    (void)group;
+    return p;
+}
+
+// signed digit of window w; `carry` threads through windows 0..W-1 in order
+__device__ __forceinline__ int msm_digit(const uint64_t s[4], int w, int c, int W, uint32_t& carry) {
+    int bit = w * c;
+    uint64_t raw = 0;
+    if (bit < 256) {
+        int limb = bit >> 6, sh = bit & 63;
+        raw = s[limb] >> sh;
+        if (sh + c > 64 && limb + 1 < 4) raw |= s[limb + 1] << (64 - sh);
+    }
+    uint32_t coef = (uint32_t)(raw & ((1u << c) - 1)) + carry;
+    if (w == W - 1) {
+        carry = 0;
+        return (int)coef;
+    }
+    carry = (coef + (1u << (c - 1))) >> c;
+    return (int)coef - (int)(carry << c);
+}
+
+template <class Fr>
+__global__ void k_scalars_from_mont(const Scalar256* in, Scalar256* out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) x.r.v[k] = in[i].v[k];
+    x = x.from_mont();
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[i].v[k] = x.r.v[k];
+}
+
+static __global__ void k_msm_hist(const Scalar256* sc, size_t n, int c, int W, uint32_t B, uint32_t* hist) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s[4] = {sc[i].v[0], sc[i].v[1], sc[i].v[2], sc[i].v[3]};
+    if ((s[0] | s[1] | s[2] | s[3]) == 0) return;
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        int d = msm_digit(s, w, c, W, carry);
+        if (d != 0) atomicAdd(&hist[(size_t)w * B + (uint32_t)(abs(d) - 1)], 1u);
+    }
+}
+
+static __global__ void k_msm_scatter(const Scalar256* sc, size_t n, int c, int W, uint32_t B, uint32_t* cursor,
+                              uint32_t* items, uint32_t* keys) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t s[4] = {sc[i].v[0], sc[i].v[1], sc[i].v[2], sc[i].v[3]};
+    if ((s[0] | s[1] | s[2] | s[3]) == 0) return;
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+        int d = msm_digit(s, w, c, W, carry);
+        if (d != 0) {
+            uint32_t key = (uint32_t)w * B + (uint32_t)(abs(d) - 1);
+            uint32_t pos = atomicAdd(&cursor[key], 1u);
+            items[pos] = ((uint32_t)i << 1) | (d < 0 ? 1u : 0u);
+            keys[pos] = key;
+        }
+    }
+}
+
+// ---- exclusive scan (u32), in place; total written to *total --------------------------------
+static constexpr int SCAN_TPB = 256;
+static constexpr int SCAN_IPT = 8;
+static constexpr int SCAN_TILE = SCAN_TPB * SCAN_IPT;
+
+static __global__ void k_scan_tiles(uint32_t* data, size_t len, uint32_t* tile_sums) {
+    __shared__ uint32_t sh[SCAN_TPB];
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_IPT;
+    uint32_t v[SCAN_IPT];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) {
+        v[k] = (base + k < len) ? data[base + k] : 0;
+        s += v[k];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the per-thread sums
+    for (int off = 1; off < SCAN_TPB; off <<= 1) {
+        uint32_t t = (threadIdx.x >= off) ? sh[threadIdx.x - off] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t excl = sh[threadIdx.x] - s;
+    if (threadIdx.x == SCAN_TPB - 1) tile_sums[blockIdx.x] = sh[threadIdx.x];
+    uint32_t run = excl;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) {
+        if (base + k < len) data[base + k] = run;
+        run += v[k];
+    }
+}
+
+static __global__ void k_scan_sums(uint32_t* tile_sums, size_t ntiles, uint32_t* total) {
+    // single block, sequential over chunks of blockDim
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t base = 0; base < ntiles; base += blockDim.x) {
+        size_t i = base + threadIdx.x;
+        uint32_t v = (i < ntiles) ? tile_sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+            uint32_t t = (threadIdx.x >= (unsigned)off) ? sh[threadIdx.x - off] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        uint32_t incl = sh[threadIdx.x];
+        if (i < ntiles) tile_sums[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+
+static __global__ void k_scan_add(uint32_t* data, size_t len, const uint32_t* tile_sums) {
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_IPT;
+    uint32_t add = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++)
+        if (base + k < len) data[base + k] += add;
+}
+
+inline void exclusive_scan_u32(hk_ctx* ctx, uint32_t* d, size_t len, uint32_t* d_total) {
+    size_t ntiles = (len + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t* sums = ctx->ws_scan.as<uint32_t>(ntiles + 1);
+    k_scan_tiles<<<(unsigned)ntiles, SCAN_TPB, 0, ctx->stream>>>(d, len, sums);
+    HK_LAUNCH_CHECK(ctx);
+    k_scan_sums<<<1, 1024, 0, ctx->stream>>>(sums, ntiles, d_total);
+    HK_LAUNCH_CHECK(ctx);
+    k_scan_add<<<(unsigned)ntiles, SCAN_TPB, 0, ctx->stream>>>(d, len, sums);
+    HK_LAUNCH_CHECK(ctx);
+}
+
+// ---- bucket accumulation ---------------------------------------------------------------------
+// Level 0: thread t owns items [t*S, (t+1)*S) of the key-sorted list (mixed adds of affine
+// bases).  Runs strictly inside the segment are complete -> bucket array.  The first and the
+// last run of a segment may continue in a neighbour -> partial list slots 2t, 2t+1
+// (key = 0xffffffff marks an empty slot).
+static constexpr uint32_t KEY_NONE = 0xffffffffu;
+
+template <class F, int S>
+__global__ void __launch_bounds__(128)
+k_msm_accum(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ items,
+            const uint32_t* __restrict__ keys, const uint32_t* __restrict__ d_count, XYZZ<F>* buckets,
+            XYZZ<F>* partial, uint32_t* partial_keys, uint32_t nthreads) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    uint32_t count = *d_count;
+    size_t lo = (size_t)t * S;
+    uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
+    if (lo < count) {
+        size_t hi = lo + S < count ? lo + S : count;
+        uint32_t cur = keys[lo];
+        uint32_t first_key = cur;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        bool first_done = false;
+        for (size_t i = lo; i < hi; i++) {
+            uint32_t k = keys[i];
+            if (k != cur) {
+                if (!first_done) {
+                    partial[2 * (size_t)t] = acc;
+                    first_done = true;
+                } else {
+                    buckets[cur] = acc;
+                }
+                acc = XYZZ<F>::inf();
+                cur = k;
+            }
+            uint32_t it = items[i];
+            Affine<F> p = bases[it >> 1];
+            acc.madd(p, it & 1);
+        }
+        k0 = first_key;
+        if (!first_done) {
+            partial[2 * (size_t)t] = acc;     // whole segment is one run
+        } else {
+            partial[2 * (size_t)t + 1] = acc;
+            k1 = cur;
+        }
+    }
+    partial_keys[2 * (size_t)t] = k0;
+    partial_keys[2 * (size_t)t + 1] = k1;
+}
+
+// Level >= 1: same scheme over a list of XYZZ partials (full adds); empty slots skipped.
+// `final_level`: single thread range covers everything -> all runs are complete.
+template <class F, int S>
+__global__ void __launch_bounds__(128)
+k_msm_fold(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys, uint32_t n_in,
+           XYZZ<F>* buckets, XYZZ<F>* out, uint32_t* out_keys, uint32_t nthreads, int final_level) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    size_t lo = (size_t)t * S;
+    size_t hi = lo + S < n_in ? lo + S : n_in;
+    uint32_t cur = KEY_NONE, first_key = KEY_NONE;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    bool first_done = false;
+    for (size_t i = lo; i < hi; i++) {
+        uint32_t k = in_keys[i];
+        if (k == KEY_NONE) continue;
+        if (cur == KEY_NONE) {
+            cur = k;
+            first_key = k;
+        } else if (k != cur) {
+            if (!first_done && !final_level) {
+                out[2 * (size_t)t] = acc;
+                first_done = true;
+            } else {
+                buckets[cur] = acc;
+                first_done = true;
+            }
+            acc = XYZZ<F>::inf();
+            cur = k;
+        }
+        acc.add(in[i]);
+    }
+    uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
+    if (cur != KEY_NONE) {
+        if (final_level) {
+            buckets[cur] = acc;
+        } else if (!first_done) {
+            out[2 * (size_t)t] = acc;
+            k0 = first_key;
+        } else {
+            out[2 * (size_t)t + 1] = acc;
+            k0 = first_key;
+            k1 = cur;
+        }
+    }
+    if (!final_level) {
+        out_keys[2 * (size_t)t] = k0;
+        out_keys[2 * (size_t)t + 1] = k1;
+    }
+}
+
+// ---- bucket reduction ------------------------------------------------------------------------
+// chunk t of window w covers bucket values v = tG+1 .. tG+G (array index v-1):
+//   sum v*B_v = sum (v - tG)*B_v + tG * sum B_v = acc + (tG)*run
+template <class F>
+__global__ void __launch_bounds__(128)
+k_msm_reduce_chunks(const XYZZ<F>* __restrict__ buckets, uint32_t B, uint32_t G, uint32_t T, uint32_t W,
+                    XYZZ<F>* chunk_out) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= T * W) return;
+    uint32_t w = g / T, t = g % T;
+    const XYZZ<F>* bk = buckets + (size_t)w * B + (size_t)t * G;
+    XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+    for (int j = (int)G - 1; j >= 0; j--) {
+        XYZZ<F> b = bk[j];
+        run.add(b);
+        acc.add(run);
+    }
+    if (t != 0) {
+        XYZZ<F> sc = run.mul_small(t * G);
+        acc.add(sc);
+    }
+    chunk_out[g] = acc;
+}
+
+template <class F, int TPB>
+__global__ void __launch_bounds__(TPB)
+k_msm_window_sum(const XYZZ<F>* __restrict__ chunks, uint32_t T, XYZZ<F>* wsum) {
+    extern __shared__ unsigned char smem_raw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    uint32_t w = blockIdx.x;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = threadIdx.x; i < T; i += TPB) acc.add(chunks[(size_t)w * T + i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = TPB / 2; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+            XYZZ<F> a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + off]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) wsum[w] = sh[0];
+}
+
+template <class F>
+__global__ void k_msm_combine(const XYZZ<F>* __restrict__ wsum, int W, int c, Jacobian<F>* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ<F> acc = wsum[W - 1];
+    for (int w = W - 2; w >= 0; w--) {
+        for (int k = 0; k < c; k++) acc = acc.dbl();
+        acc.add(wsum[w]);
+    }
+    *out = Jacobian<F>::from_xyzz(acc);
+}
+
+template <class F>
+__global__ void k_set_identity_jac(Jacobian<F>* out, size_t K) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < K) out[i] = {F::one(), F::one(), F::zero()};
+}
+
+template <class Curve, int GROUP>
+void msm_run(hk_ctx* ctx, const void* d_bases_v, size_t n, const Scalar256* d_scalars_in, size_t K,
+             bool scalars_mont, void* d_out_jac_v) {
+    using F = typename GroupFieldT<Curve, GROUP>::F;
+    using Fr = typename Curve::Fr;
+    const Affine<F>* d_bases = reinterpret_cast<const Affine<F>*>(d_bases_v);
+    Jacobian<F>* d_out = reinterpret_cast<Jacobian<F>*>(d_out_jac_v);
+    cudaStream_t st = ctx->stream;
+    if (K == 0) return;
+    if (n == 0) {
+        k_set_identity_jac<F><<<ceil_div(K, 128), 128, 0, st>>>(d_out, K);
+        HK_LAUNCH_CHECK(ctx);
+        return;
+    }
+    HK_REQUIRE(n < (size_t(1) << 31), HK_ERR_UNSUPPORTED, "msm: n must be < 2^31");
+    MsmPlan pl = msm_plan(n, Curve::FR_BITS, GROUP);
+    const size_t nkeys = (size_t)pl.W * pl.B;
+    const size_t max_items = n * (size_t)pl.W;
+    HK_REQUIRE(max_items < (size_t(1) << 32), HK_ERR_UNSUPPORTED, "msm: n * windows must be < 2^32");
+    constexpr int S0 = 32;   // level-0 segment length
+    constexpr int S1 = 16;   // fold segment length
+
+    const Scalar256* d_sc_all = d_scalars_in;
+    if (scalars_mont) {
+        Scalar256* conv = ctx->ws_scalars.as<Scalar256>(n * K);
+        k_scalars_from_mont<Fr><<<ceil_div(n * K, 256), 256, 0, st>>>(d_scalars_in, conv, n * K);
+        HK_LAUNCH_CHECK(ctx);
+        d_sc_all = conv;
+    }
+    uint32_t* hist = ctx->ws_hist.as<uint32_t>(nkeys + 4);
+    uint32_t* d_count = hist + nkeys;     // total item count lives right after the histogram
+    uint32_t* items = ctx->ws_items.as<uint32_t>(2 * max_items);
+    uint32_t* keys = items + max_items;
+    XYZZ<F>* buckets = ctx->ws_buckets.as<XYZZ<F>>(nkeys);
+    const uint32_t nthr0 = ceil_div(max_items, S0);
+    // partial lists: level sizes 2*nthr0, then shrink by S1/2 each level
+    std::vector<uint32_t> lvl_in;      // entries consumed at fold level l
+    {
+        uint32_t cur = 2 * nthr0;
+        while (true) {
+            lvl_in.push_back(cur);
+            uint32_t thr = ceil_div(cur, S1);
+            if (thr <= 1) break;
+            cur = 2 * thr;
+        }
+    }
+    size_t part_total = 0;
+    for (uint32_t v : lvl_in) part_total += v;
+    XYZZ<F>* partial = ctx->ws_chunks.as<XYZZ<F>>(part_total);
+    uint32_t* partial_keys = ctx->ws_misc.as<uint32_t>(part_total);
+    // reduction geometry
+    uint32_t G = pl.B >= 2048 ? 16 : (pl.B >= 64 ? 4 : 1);
+    uint32_t T = pl.B / G;
+    XYZZ<F>* chunk_out = ctx->ws_wsum.as<XYZZ<F>>((size_t)T * pl.W + pl.W);
+    XYZZ<F>* wsum = chunk_out + (size_t)T * pl.W;
+
+    for (size_t k = 0; k < K; k++) {
+        const Scalar256* d_sc = d_sc_all + k * n;
+        HK_CUDA(cudaMemsetAsync(hist, 0, (nkeys + 4) * sizeof(uint32_t), st));
+        HK_CUDA(cudaMemsetAsync(buckets, 0, nkeys * sizeof(XYZZ<F>), st));
+        k_msm_hist<<<ceil_div(n, 256), 256, 0, st>>>(d_sc, n, pl.c, pl.W, pl.B, hist);
+        HK_LAUNCH_CHECK(ctx);
+        exclusive_scan_u32(ctx, hist, nkeys, d_count);
+        k_msm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(d_sc, n, pl.c, pl.W, pl.B, hist, items, keys);
+        HK_LAUNCH_CHECK(ctx);
+        k_msm_accum<F, S0><<<ceil_div(nthr0, 128), 128, 0, st>>>(d_bases, items, keys, d_count, buckets, partial,
+                                                               partial_keys, nthr0);
+        HK_LAUNCH_CHECK(ctx);
+        size_t off = 0;
+        for (size_t l = 0; l < lvl_in.size(); l++) {
+            uint32_t n_in = lvl_in[l];
+            uint32_t thr = ceil_div(n_in, S1);
+            int final_level = (l + 1 == lvl_in.size());
+            XYZZ<F>* in = partial + off;
+            uint32_t* in_keys = partial_keys + off;
+            XYZZ<F>* out = partial + off + n_in;
+            uint32_t* out_keys = partial_keys + off + n_in;
+            k_msm_fold<F, S1><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr,
+                                                                final_level);
+            HK_LAUNCH_CHECK(ctx);
+            off += n_in;
+        }
+        k_msm_reduce_chunks<F><<<ceil_div((size_t)T * pl.W, 128), 128, 0, st>>>(buckets, pl.B, G, T, pl.W, chunk_out);
+        HK_LAUNCH_CHECK(ctx);
+        constexpr int WS_TPB = 64;
+        k_msm_window_sum<F, WS_TPB><<<pl.W, WS_TPB, WS_TPB * sizeof(XYZZ<F>), st>>>(chunk_out, T, wsum);
+        HK_LAUNCH_CHECK(ctx);
+        k_msm_combine<F><<<1, 32, 0, st>>>(wsum, pl.W, pl.c, d_out + k);
+        HK_LAUNCH_CHECK(ctx);
+    }
+}
+
+}  // namespace hk

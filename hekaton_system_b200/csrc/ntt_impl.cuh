@@ -1,0 +1,398 @@
+// Radix-2 NTT over Fr for sm_100a.  Replaces ark-poly 0.4 `Radix2EvaluationDomain::
+// {fft_in_place, ifft_in_place}` (+ `get_coset(F::GENERATOR)`), which the reference reaches through
+// `QAP::witness_map` at /root/reference/cp-groth16/src/prover.rs:123.
+//
+// Domain conventions: size N = 2^log_n, group_gen = TWO_ADIC_ROOT^(2^(S-log_n)),
+// forward out[k] = sum_j x_j w^(jk) (natural order in and out), inverse includes 1/N, coset
+// forward pre-multiplies x_i by g^i, coset inverse post-multiplies by g^-i.
+//
+// Kernel structure: a transform is 1-3 passes; each pass runs up to 11 butterfly stages on a
+// 2^T-element tile staged in shared memory (two 16-byte half-element planes so that unit-stride
+// LDS.128/STS.128 are conflict free), reading and writing global memory once.  Tiles of the
+// strided passes take 2^q consecutive elements per row (q = 2: 128-byte contiguous runs).
+//   DIF pass: stages ascending, (u,v) -> (u+v, (u-v)w)   natural in -> bit-reversed out
+//   DIT pass: stages descending, (u,v) -> (u+vw, u-vw)   bit-reversed in -> natural out
+// Bit-reversal, coset scaling and 1/N are folded into the first/last pass (PERM_IN/PERM_OUT,
+// pre/post scale tables).  Twiddles come from a per-stage compacted table
+// tw[off_s + j] = root^(j 2^s), off_s = N - (N >> s), so stage s reads a contiguous range.
+#pragma once
+#include "common.cuh"
+
+namespace hk {
+
+template <class Curve>
+struct FrConsts;
+template <>
+struct FrConsts<Bls12381> {
+    using Fr = Bls12381::Fr;
+    __device__ static Fr root() {
+        Fr x;
+        for (int i = 0; i < 4; i++) x.r.v[i] = bls12_381_fr_ROOT[i];
+        return x;
+    }
+    __device__ static Fr gen() {
+        Fr x;
+        for (int i = 0; i < 4; i++) x.r.v[i] = bls12_381_fr_GEN[i];
+        return x;
+    }
+};
+template <>
+struct FrConsts<Bn254> {
+    using Fr = Bn254::Fr;
+    __device__ static Fr root() {
+        Fr x;
+        for (int i = 0; i < 4; i++) x.r.v[i] = bn254_fr_ROOT[i];
+        return x;
+    }
+    __device__ static Fr gen() {
+        Fr x;
+        for (int i = 0; i < 4; i++) x.r.v[i] = bn254_fr_GEN[i];
+        return x;
+    }
+};
+
+static constexpr uint32_t NTT_TMAX = 11;   // tile = 2^11 elements = 64 KiB of shared memory
+static constexpr uint32_t NTT_QMAX = 2;
+static constexpr uint32_t NTT_TPB = 512;
+
+enum : uint32_t { NTT_PERM_IN = 1, NTT_PERM_OUT = 2 };
+
+struct NttDomain {
+    uint32_t log_n = 0;
+    DevBuf buf;
+    // all tables hold N (or N-1) Fr elements
+    void* tw_fwd = nullptr;        // root = w
+    void* tw_inv = nullptr;        // root = w^-1
+    void* coset_nat = nullptr;     // g^i
+    void* coset_inv_nat = nullptr; // g^-i / N
+    void* coset_br = nullptr;      // g^rev(p) / N          (pipeline: unnormalised DIF output -> coset DIT input)
+    void* coset_inv_br = nullptr;  // g^-rev(p) / N         (pipeline: last DIF output -> natural h)
+    void* n_inv = nullptr;         // single element 1/N
+    void* zh_inv = nullptr;        // single element 1/(g^N - 1)
+};
+
+struct NttPass {
+    uint32_t s0, k, q, T;
+};
+
+inline std::vector<NttPass> ntt_plan(uint32_t log_n) {
+    std::vector<NttPass> p;
+    if (log_n == 0) return p;
+    if (log_n <= NTT_TMAX) {
+        p.push_back({0, log_n, 0, log_n});
+        return p;
+    }
+    uint32_t last = NTT_TMAX;
+    uint32_t rest = log_n - last;
+    uint32_t per = NTT_TMAX - NTT_QMAX;
+    uint32_t np = (rest + per - 1) / per;
+    uint32_t s = 0;
+    for (uint32_t i = 0; i < np; i++) {
+        uint32_t k = rest / np + (i < rest % np ? 1 : 0);
+        uint32_t L = log_n - s - k;
+        uint32_t q = L < NTT_QMAX ? L : NTT_QMAX;
+        p.push_back({s, k, q, NTT_TMAX});
+        s += k;
+    }
+    p.push_back({s, last, 0, NTT_TMAX});
+    return p;
+}
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return bits ? (__brev(x) >> (32 - bits)) : 0; }
+
+// shared-memory element access: two planes of 16-byte halves
+template <class Fr>
+__device__ __forceinline__ Fr sm_load(const uint4* lo, const uint4* hi, uint32_t e) {
+    uint4 a = lo[e], b = hi[e];
+    Fr x;
+    x.r.v[0] = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    x.r.v[1] = (uint64_t)a.z | ((uint64_t)a.w << 32);
+    x.r.v[2] = (uint64_t)b.x | ((uint64_t)b.y << 32);
+    x.r.v[3] = (uint64_t)b.z | ((uint64_t)b.w << 32);
+    return x;
+}
+template <class Fr>
+__device__ __forceinline__ void sm_store(uint4* lo, uint4* hi, uint32_t e, const Fr& x) {
+    lo[e] = make_uint4((uint32_t)x.r.v[0], (uint32_t)(x.r.v[0] >> 32), (uint32_t)x.r.v[1], (uint32_t)(x.r.v[1] >> 32));
+    hi[e] = make_uint4((uint32_t)x.r.v[2], (uint32_t)(x.r.v[2] >> 32), (uint32_t)x.r.v[3], (uint32_t)(x.r.v[3] >> 32));
+}
+
+// One pass.  grid = (N >> T, K).  in/out may alias when no permutation flag is set.
+template <class Fr, bool DIT>
+__global__ void __launch_bounds__(NTT_TPB)
+k_ntt_pass(const Fr* in_all, Fr* out_all, const Fr* __restrict__ tw, uint32_t log_n,
+           uint32_t s0, uint32_t k, uint32_t q, uint32_t T, const Fr* __restrict__ pre_scale,
+           const Fr* __restrict__ post_scale, const Fr* __restrict__ post_const, uint32_t flags) {
+    extern __shared__ uint4 smem[];
+    uint4* slo = smem;
+    uint4* shi = smem + (1u << T);
+    const size_t N = size_t(1) << log_n;
+    const Fr* in = in_all + (size_t)blockIdx.y * N;
+    Fr* out = out_all + (size_t)blockIdx.y * N;
+    const uint32_t L = log_n - s0 - k;
+    const uint32_t hs_bits = T - k - q;
+    const uint32_t tile = 1u << T;
+
+    auto gidx = [&](uint32_t e) -> uint32_t {
+        uint32_t lq = e & ((1u << q) - 1);
+        uint32_t m = (e >> q) & ((1u << k) - 1);
+        uint32_t hsub = e >> (q + k);
+        uint32_t outer = (blockIdx.x << hs_bits) | hsub;
+        uint32_t lhi = outer & ((1u << (L - q)) - 1);
+        uint32_t H = outer >> (L - q);
+        return (H << (k + L)) | (m << L) | (lhi << q) | lq;
+    };
+
+    for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
+        uint32_t i = gidx(e);
+        uint32_t src = (flags & NTT_PERM_IN) ? bitrev(i, log_n) : i;
+        Fr x = in[src];
+        if (pre_scale) x = x * pre_scale[src];
+        sm_store(slo, shi, e, x);
+    }
+    __syncthreads();
+
+    const uint32_t nbf = tile >> 1;
+    for (uint32_t tt = 0; tt < k; tt++) {
+        const uint32_t t = DIT ? (k - 1 - tt) : tt;      // stage offset within the pass
+        const uint32_t s = s0 + t;
+        const uint32_t mb = k - 1 - t;                    // bit of m toggled by this stage
+        const uint32_t pos = q + mb;
+        const size_t off_s = N - (N >> s);
+        for (uint32_t bf = threadIdx.x; bf < nbf; bf += blockDim.x) {
+            uint32_t e0 = ((bf >> pos) << (pos + 1)) | (bf & ((1u << pos) - 1));
+            uint32_t e1 = e0 | (1u << pos);
+            uint32_t i0 = gidx(e0);
+            uint32_t j = i0 & ((1u << (L + mb)) - 1);
+            Fr w = tw[off_s + j];
+            Fr u = sm_load<Fr>(slo, shi, e0);
+            Fr v = sm_load<Fr>(slo, shi, e1);
+            if (DIT) {
+                v = v * w;
+                sm_store(slo, shi, e0, u + v);
+                sm_store(slo, shi, e1, u - v);
+            } else {
+                sm_store(slo, shi, e0, u + v);
+                sm_store(slo, shi, e1, (u - v) * w);
+            }
+        }
+        __syncthreads();
+    }
+
+    Fr pc;
+    if (post_const) pc = *post_const;
+    for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
+        uint32_t i = gidx(e);
+        uint32_t dst = (flags & NTT_PERM_OUT) ? bitrev(i, log_n) : i;
+        Fr x = sm_load<Fr>(slo, shi, e);
+        if (post_scale) x = x * post_scale[dst];
+        if (post_const) x = x * pc;
+        out[dst] = x;
+    }
+}
+
+// ---- table construction (one-off per (context, log_n)) ------------------------------------------
+// pw[b] = base^(2^b), b < nb  (single thread)
+template <class Fr>
+__global__ void k_pow2_table(Fr base, Fr* pw, uint32_t nb) {
+    if (threadIdx.x || blockIdx.x) return;
+    Fr x = base;
+    for (uint32_t b = 0; b < nb; b++) {
+        pw[b] = x;
+        x = x.sqr();
+    }
+}
+
+template <class Fr>
+__device__ __forceinline__ Fr pow_from_table(const Fr* pw, uint32_t e) {
+    Fr acc = Fr::one();
+    for (uint32_t b = 0; e; b++, e >>= 1)
+        if (e & 1) acc = acc * pw[b];
+    return acc;
+}
+
+// out[i] = mult * base^(perm(i) * stride), i < n ; perm = bitrev over `bits` when bits > 0
+template <class Fr>
+__global__ void k_pow_fill(const Fr* pw, Fr* out, uint32_t n, uint32_t stride_log, uint32_t br_bits,
+                           const Fr* mult) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t e = br_bits ? bitrev(i, br_bits) : i;
+    // exponent e << stride_log can exceed 32 bits only if stride_log + log2(n) > 32; callers keep it <= 32
+    uint64_t ee = (uint64_t)e << stride_log;
+    Fr acc = Fr::one();
+    for (uint32_t b = 0; ee; b++, ee >>= 1)
+        if (ee & 1) acc = acc * pw[b];
+    if (mult) acc = acc * (*mult);
+    out[i] = acc;
+}
+
+// scalars: [0] = w_N, [1] = w_N^-1, [2] = g, [3] = g^-1, [4] = 1/N, [5] = 1/(g^N - 1)
+template <class Curve>
+__global__ void k_domain_scalars(typename Curve::Fr* sc, uint32_t log_n) {
+    using Fr = typename Curve::Fr;
+    if (threadIdx.x || blockIdx.x) return;
+    Fr w = FrConsts<Curve>::root();
+    for (uint32_t i = log_n; i < (uint32_t)Curve::TWO_ADICITY; i++) w = w.sqr();
+    Fr g = FrConsts<Curve>::gen();
+    sc[0] = w;
+    sc[1] = w.inverse();
+    sc[2] = g;
+    sc[3] = g.inverse();
+    // N in Montgomery form: one() doubled log_n times
+    Fr nn = Fr::one();
+    for (uint32_t i = 0; i < log_n; i++) nn = nn.dbl();
+    sc[4] = nn.inverse();
+    Fr gN = g;
+    for (uint32_t i = 0; i < log_n; i++) gN = gN.sqr();
+    sc[5] = (gN - Fr::one()).inverse();
+}
+
+template <class Curve>
+std::shared_ptr<NttDomain> ntt_domain(hk_ctx* ctx, uint32_t log_n) {
+    using Fr = typename Curve::Fr;
+    auto it = ctx->domains.find(log_n);
+    if (it != ctx->domains.end()) return it->second;
+    HK_REQUIRE(log_n <= (uint32_t)Curve::TWO_ADICITY, HK_ERR_UNSUPPORTED,
+               "ntt: log_n exceeds the two-adicity of Fr (PolynomialDegreeTooLarge)");
+    HK_REQUIRE(log_n <= 30, HK_ERR_UNSUPPORTED, "ntt: log_n > 30 not supported");
+    auto d = std::make_shared<NttDomain>();
+    d->log_n = log_n;
+    const size_t N = size_t(1) << log_n;
+    // layout: 6 tables of N + scalars(8) + pow2 tables 4 x 40
+    Fr* base = d->buf.as<Fr>(6 * N + 8 + 4 * 40);
+    Fr* tw_fwd = base;
+    Fr* tw_inv = base + N;
+    Fr* coset_nat = base + 2 * N;
+    Fr* coset_inv_nat = base + 3 * N;
+    Fr* coset_br = base + 4 * N;
+    Fr* coset_inv_br = base + 5 * N;
+    Fr* sc = base + 6 * N;
+    Fr* pw_w = sc + 8;
+    Fr* pw_wi = pw_w + 40;
+    Fr* pw_g = pw_wi + 40;
+    Fr* pw_gi = pw_g + 40;
+    cudaStream_t st = ctx->stream;
+    k_domain_scalars<Curve><<<1, 1, 0, st>>>(sc, log_n);
+    HK_LAUNCH_CHECK(ctx);
+    // the pow2 kernels take their base by value from device memory -> read it back (tiny, one-off)
+    Fr h[6];
+    HK_CUDA(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    HK_CUDA(cudaStreamSynchronize(st));
+    uint32_t nb = log_n + 1;
+    k_pow2_table<Fr><<<1, 1, 0, st>>>(h[0], pw_w, nb);
+    k_pow2_table<Fr><<<1, 1, 0, st>>>(h[1], pw_wi, nb);
+    k_pow2_table<Fr><<<1, 1, 0, st>>>(h[2], pw_g, nb);
+    k_pow2_table<Fr><<<1, 1, 0, st>>>(h[3], pw_gi, nb);
+    ctx->launches += 4;
+    HK_CUDA(cudaGetLastError());
+    for (uint32_t s = 0; s < log_n; s++) {
+        uint32_t hs = (uint32_t)(N >> (s + 1));
+        size_t off = N - (N >> s);
+        k_pow_fill<Fr><<<ceil_div(hs, 256), 256, 0, st>>>(pw_w, tw_fwd + off, hs, s, 0, nullptr);
+        k_pow_fill<Fr><<<ceil_div(hs, 256), 256, 0, st>>>(pw_wi, tw_inv + off, hs, s, 0, nullptr);
+        ctx->launches += 2;
+    }
+    HK_CUDA(cudaGetLastError());
+    uint32_t n32 = (uint32_t)N;
+    k_pow_fill<Fr><<<ceil_div(N, 256), 256, 0, st>>>(pw_g, coset_nat, n32, 0, 0, nullptr);
+    k_pow_fill<Fr><<<ceil_div(N, 256), 256, 0, st>>>(pw_gi, coset_inv_nat, n32, 0, 0, sc + 4);
+    k_pow_fill<Fr><<<ceil_div(N, 256), 256, 0, st>>>(pw_g, coset_br, n32, 0, log_n, sc + 4);
+    k_pow_fill<Fr><<<ceil_div(N, 256), 256, 0, st>>>(pw_gi, coset_inv_br, n32, 0, log_n, sc + 4);
+    ctx->launches += 4;
+    HK_CUDA(cudaGetLastError());
+    d->tw_fwd = tw_fwd;
+    d->tw_inv = tw_inv;
+    d->coset_nat = coset_nat;
+    d->coset_inv_nat = coset_inv_nat;
+    d->coset_br = coset_br;
+    d->coset_inv_br = coset_inv_br;
+    d->n_inv = sc + 4;
+    d->zh_inv = sc + 5;
+    ctx->domains[log_n] = d;
+    return d;
+}
+
+// Launch all passes of one transform.
+//   dit = false: DIF (natural -> bit-reversed), passes in plan order
+//   dit = true : DIT (bit-reversed -> natural), passes in reverse plan order
+// src -> dst; `tmp` is used when a permutation forces out-of-place passes.
+template <class Curve>
+void ntt_passes(hk_ctx* ctx, const NttDomain& d, bool dit, bool inverse_root, const typename Curve::Fr* src,
+                typename Curve::Fr* dst, typename Curve::Fr* tmp, size_t K, bool perm_in, bool perm_out,
+                const typename Curve::Fr* pre_scale, const typename Curve::Fr* post_scale,
+                const typename Curve::Fr* post_const, bool src_clobber_ok = false) {
+    using Fr = typename Curve::Fr;
+    const uint32_t log_n = d.log_n;
+    auto plan = ntt_plan(log_n);
+    const Fr* tw = reinterpret_cast<const Fr*>(inverse_root ? d.tw_inv : d.tw_fwd);
+    const size_t np = plan.size();
+    if (dit)
+        HK_CUDA(cudaFuncSetAttribute(k_ntt_pass<Fr, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    else
+        HK_CUDA(cudaFuncSetAttribute(k_ntt_pass<Fr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    // Buffer routing.  A pass carrying a permutation must run out of place; any other pass may
+    // run in place.  `src` is only overwritten when src == dst or the caller allows it.
+    const Fr* cur = src;
+    for (size_t pi = 0; pi < np; pi++) {
+        const NttPass& ps = dit ? plan[np - 1 - pi] : plan[pi];
+        bool first = (pi == 0), last = (pi + 1 == np);
+        uint32_t flags = 0;
+        if (first && perm_in) flags |= NTT_PERM_IN;
+        if (last && perm_out) flags |= NTT_PERM_OUT;
+        const bool oop = flags != 0;
+        Fr* to;
+        if (last) {
+            to = dst;
+            if (oop && cur == dst) to = tmp;          // copied back below
+        } else if (oop) {
+            to = (cur == tmp) ? dst : tmp;
+        } else if (cur == src && src != dst && !src_clobber_ok) {
+            to = dst;
+        } else {
+            to = const_cast<Fr*>(cur);
+        }
+        dim3 grid((unsigned)((size_t(1) << log_n) >> ps.T), (unsigned)K);
+        size_t smem = (size_t(2) << ps.T) * sizeof(uint4);
+        const Fr* pre = first ? pre_scale : nullptr;
+        const Fr* post = last ? post_scale : nullptr;
+        const Fr* pc = last ? post_const : nullptr;
+        if (dit)
+            k_ntt_pass<Fr, true><<<grid, NTT_TPB, smem, ctx->stream>>>(cur, to, tw, log_n, ps.s0, ps.k, ps.q, ps.T, pre,
+                                                                       post, pc, flags);
+        else
+            k_ntt_pass<Fr, false><<<grid, NTT_TPB, smem, ctx->stream>>>(cur, to, tw, log_n, ps.s0, ps.k, ps.q, ps.T, pre,
+                                                                        post, pc, flags);
+        HK_LAUNCH_CHECK(ctx);
+        cur = to;
+    }
+    if (cur != dst) {
+        HK_CUDA(cudaMemcpyAsync(dst, cur, (K << log_n) * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+}
+
+template <class Curve>
+void ntt_run(hk_ctx* ctx, uint64_t* d_data, uint32_t log_n, size_t K, uint32_t dir, uint32_t domain) {
+    using Fr = typename Curve::Fr;
+    if (K == 0) return;
+    Fr* data = reinterpret_cast<Fr*>(d_data);
+    if (log_n == 0) {
+        return;   // size-1 transform is the identity in both directions (offset^0 = 1, 1/N = 1)
+    }
+    auto dom = ntt_domain<Curve>(ctx, log_n);
+    const size_t N = size_t(1) << log_n;
+    Fr* tmp = ctx->ws_ntt_tmp.as<Fr>(N * K);
+    const bool coset = (domain == HK_DOMAIN_COSET_GENERATOR);
+    if (dir == HK_NTT_FORWARD) {
+        // DIT(w) with bit-reversed loads; coset: x_j *= g^j at load (index = source position)
+        ntt_passes<Curve>(ctx, *dom, true, false, data, data, tmp, K, true, false,
+                          coset ? reinterpret_cast<const Fr*>(dom->coset_nat) : nullptr, nullptr, nullptr);
+    } else {
+        // DIT(w^-1) with bit-reversed loads, then * 1/N (plain) or * g^-k / N (coset) at the store
+        ntt_passes<Curve>(ctx, *dom, true, true, data, data, tmp, K, true, false, nullptr,
+                          coset ? reinterpret_cast<const Fr*>(dom->coset_inv_nat) : nullptr,
+                          coset ? nullptr : reinterpret_cast<const Fr*>(dom->n_inv));
+    }
+}
+
+}  // namespace hk

@@ -1,0 +1,370 @@
+// Fused per-subcircuit CP-Groth16 path on the device.
+//   commit : /root/reference/cp-groth16/src/committer.rs:55-98
+//   prove  : /root/reference/cp-groth16/src/committer.rs:100-122 -> prover.rs:19-32,53-156
+//
+// Every O(1) group operation of the reference that has a FIXED base is folded into the
+// neighbouring MSM as an extra (base, scalar) pair, so no serial scalar multiplication is
+// paid for it:
+//   A   = MSM( [a_g[1..], a_g[0], alpha_g, delta_g] , [z[1..], 1, 1, r] )        prover.rs:86-88,158-171
+//   B1  = MSM( [b_g[1..], b_g[0], beta_g,  delta_g] , [z[1..], 1, 1, s] )        prover.rs:94-97
+//   B2  = MSM( [b_h[1..], b_h[0], beta_h,  delta_h] , [z[1..], 1, 1, s] )  (G2)  prover.rs:106-107
+//   L'  = MSM( [ck_last.., delta_g, deltas_g[0..]]  , [w_last.., -rs, -kappa_i] ) prover.rs:117,135,144; committer.rs:113-114
+//   H   = MSM( h_g , h[..N-1] )                                                  prover.rs:128-129
+//   C   = s*A + r*B1 + L' + H                                                    prover.rs:139-147
+// Only s*A and r*B1 (scalar times a freshly computed point) remain as scalar
+// multiplications; k_prove_finish runs them on two warps and normalises A, B2, C.
+// (r == 0 needs no special case: the reference sets B1 = 0 only to skip work, r*B1 is 0.)
+#include "prove.cuh"
+
+#include "ntt_impl.cuh"
+#include "qap.cuh"
+
+namespace hk {
+
+// ---- small generic kernels --------------------------------------------------------------------
+template <class F>
+__global__ void k_apply_infinity(Affine<F>* pts, const uint8_t* inf, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (inf[i]) pts[i] = Affine<F>::inf();
+}
+
+template <class F>
+__global__ void k_jac_to_affine(const Jacobian<F>* in, Affine<F>* out, uint8_t* inf, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> p = in[i].to_xyzz();
+    Affine<F> a = p.to_affine();
+    out[i] = a;
+    if (inf) inf[i] = p.is_inf() ? 1 : 0;
+}
+
+// k * P, k a canonical 256-bit integer, 4-bit fixed windows (MSB first)
+template <class F>
+__device__ __noinline__ XYZZ<F> scalar_mul(const XYZZ<F>& p, const uint64_t k[4]) {
+    XYZZ<F> tbl[16];
+    tbl[0] = XYZZ<F>::inf();
+    tbl[1] = p;
+    for (int i = 2; i < 16; i++) {
+        tbl[i] = tbl[i - 1];
+        tbl[i].add(p);
+    }
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int w = 63; w >= 0; w--) {
+        for (int j = 0; j < 4; j++) acc = acc.dbl();
+        uint32_t d = (uint32_t)(k[w >> 4] >> ((w & 15) * 4)) & 15u;
+        if (d) acc.add(tbl[d]);
+    }
+    return acc;
+}
+
+// Fixed-base table T[w][d] = d * 16^w * G  (w < 64, d < 16), then out[i] = sum_w T[w][digit_w(k_i)]
+template <class F>
+__global__ void k_fixed_table(const Affine<F>* gen, XYZZ<F>* tbl) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= 64) return;
+    XYZZ<F> b = XYZZ<F>::from_affine(*gen);
+    for (uint32_t i = 0; i < 4 * w; i++) b = b.dbl();
+    XYZZ<F> acc = XYZZ<F>::inf();
+    tbl[w * 16] = acc;
+    for (int d = 1; d < 16; d++) {
+        acc.add(b);
+        tbl[w * 16 + d] = acc;
+    }
+}
+
+template <class F, class Fr>
+__global__ void __launch_bounds__(128)
+k_fixed_base_mul(const XYZZ<F>* __restrict__ tbl, const Scalar256* __restrict__ sc, int mont, Affine<F>* out,
+                 size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k[4] = {sc[i].v[0], sc[i].v[1], sc[i].v[2], sc[i].v[3]};
+    if (mont) {
+        Fr x;
+        for (int j = 0; j < 4; j++) x.r.v[j] = k[j];
+        x = x.from_mont();
+        for (int j = 0; j < 4; j++) k[j] = x.r.v[j];
+    }
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int w = 0; w < 64; w++) {
+        uint32_t d = (uint32_t)(k[w >> 4] >> ((w & 15) * 4)) & 15u;
+        if (d) acc.add(tbl[w * 16 + d]);
+    }
+    out[i] = acc.to_affine();
+}
+
+// ---- scalar staging ---------------------------------------------------------------------------
+// S = from_mont([ z[1..m-1], 1, 1, x ])  (m + 2 canonical scalars)
+template <class Fr>
+__global__ void k_build_abc_scalars(const Fr* __restrict__ z, size_t m, const Fr* x, Scalar256* out) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= m + 2) return;
+    Fr v;
+    if (i < m - 1) v = z[i + 1];
+    else if (i < m + 1) v = Fr::one();
+    else v = *x;
+    v = v.from_mont();
+    for (int k = 0; k < 4; k++) out[i].v[k] = v.r.v[k];
+}
+
+template <class Fr>
+__global__ void k_patch_scalar(const Fr* x, Scalar256* dst) {
+    if (threadIdx.x || blockIdx.x) return;
+    Fr v = (*x).from_mont();
+    for (int k = 0; k < 4; k++) dst->v[k] = v.r.v[k];
+}
+
+// L' scalars (Montgomery): [ w_last (nl), -(r s), -kappa_0 .. -kappa_{ns-2} ]
+template <class Fr>
+__global__ void k_build_l_scalars(const Fr* __restrict__ w_last, size_t nl, const Fr* r, const Fr* s,
+                                  const Fr* kappas, uint32_t nk, Fr* out) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= nl + 1 + nk) return;
+    if (i < nl) out[i] = w_last[i];
+    else if (i == nl) out[i] = ((*r) * (*s)).neg();
+    else out[i] = kappas[i - nl - 1].neg();
+}
+
+// commit scalars (Montgomery): [ w_stage (nw), kappa ]
+template <class Fr>
+__global__ void k_build_commit_scalars(const Fr* __restrict__ w, size_t nw, const Fr* kappa, Fr* out) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i > nw) return;
+    out[i] = (i < nw) ? w[i] : *kappa;
+}
+
+// ---- finish -----------------------------------------------------------------------------------
+// jac[0] = A, jac[1] = B1, jac[2] = L', jac[3] = H (G1);  jacB2 (G2);  r, s Montgomery Fr.
+template <class Curve>
+__global__ void __launch_bounds__(96)
+k_prove_finish(const Jacobian<typename Curve::Fq>* jac, const Jacobian<typename Curve::Fq2>* jacB2,
+               const typename Curve::Fr* r_m, const typename Curve::Fr* s_m, Affine<typename Curve::Fq>* outA,
+               Affine<typename Curve::Fq2>* outB, Affine<typename Curve::Fq>* outC, uint8_t* inf) {
+    using Fq = typename Curve::Fq;
+    using Fq2 = typename Curve::Fq2;
+    __shared__ XYZZ<Fq> sh[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        if (warp == 0) {
+            auto s = (*s_m).from_mont();
+            sh[0] = scalar_mul<Fq>(jac[0].to_xyzz(), s.r.v);
+        } else if (warp == 1) {
+            auto r = (*r_m).from_mont();
+            sh[1] = scalar_mul<Fq>(jac[1].to_xyzz(), r.r.v);
+        } else {
+            XYZZ<Fq2> b = jacB2[0].to_xyzz();
+            *outB = b.to_affine();
+            inf[1] = b.is_inf() ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    if (lane == 0) {
+        if (warp == 0) {
+            XYZZ<Fq> c = sh[0];
+            c.add(sh[1]);
+            c.add(jac[2].to_xyzz());
+            c.add(jac[3].to_xyzz());
+            *outC = c.to_affine();
+            inf[2] = c.is_inf() ? 1 : 0;
+        } else if (warp == 1) {
+            XYZZ<Fq> a = jac[0].to_xyzz();
+            *outA = a.to_affine();
+            inf[0] = a.is_inf() ? 1 : 0;
+        }
+    }
+}
+
+// ---- host orchestration -----------------------------------------------------------------------
+template <class Curve>
+static void bases_finish_upload(hk_ctx* ctx, BaseSet& bs, const uint8_t* d_inf) {
+    if (!d_inf || bs.n == 0) return;
+    if (bs.group == 1)
+        k_apply_infinity<typename Curve::Fq><<<ceil_div(bs.n, 256), 256, 0, ctx->stream>>>(
+            reinterpret_cast<Affine<typename Curve::Fq>*>(bs.d), d_inf, bs.n);
+    else
+        k_apply_infinity<typename Curve::Fq2><<<ceil_div(bs.n, 256), 256, 0, ctx->stream>>>(
+            reinterpret_cast<Affine<typename Curve::Fq2>*>(bs.d), d_inf, bs.n);
+    HK_LAUNCH_CHECK(ctx);
+}
+
+template <class Curve>
+void apply_infinity(hk_ctx* ctx, BaseSet& bs, const uint8_t* d_inf) {
+    bases_finish_upload<Curve>(ctx, bs, d_inf);
+}
+template void apply_infinity<Bls12381>(hk_ctx*, BaseSet&, const uint8_t*);
+template void apply_infinity<Bn254>(hk_ctx*, BaseSet&, const uint8_t*);
+
+template <class Curve, int GROUP>
+void jac_to_affine(hk_ctx* ctx, const void* d_jac, void* d_aff, uint8_t* d_inf, size_t n) {
+    using F = typename GroupFieldT<Curve, GROUP>::F;
+    if (n == 0) return;
+    k_jac_to_affine<F><<<ceil_div(n, 64), 64, 0, ctx->stream>>>(reinterpret_cast<const Jacobian<F>*>(d_jac),
+                                                                reinterpret_cast<Affine<F>*>(d_aff), d_inf, n);
+    HK_LAUNCH_CHECK(ctx);
+}
+template void jac_to_affine<Bls12381, 1>(hk_ctx*, const void*, void*, uint8_t*, size_t);
+template void jac_to_affine<Bls12381, 2>(hk_ctx*, const void*, void*, uint8_t*, size_t);
+template void jac_to_affine<Bn254, 1>(hk_ctx*, const void*, void*, uint8_t*, size_t);
+template void jac_to_affine<Bn254, 2>(hk_ctx*, const void*, void*, uint8_t*, size_t);
+
+template <class Curve, int GROUP>
+void fixed_base_mul(hk_ctx* ctx, const void* d_gen_affine, const Scalar256* d_scalars, size_t n, bool mont,
+                    void* d_out_affine) {
+    using F = typename GroupFieldT<Curve, GROUP>::F;
+    using Fr = typename Curve::Fr;
+    if (n == 0) return;
+    XYZZ<F>* tbl = ctx->ws_misc.as<XYZZ<F>>(64 * 16);
+    k_fixed_table<F><<<2, 32, 0, ctx->stream>>>(reinterpret_cast<const Affine<F>*>(d_gen_affine), tbl);
+    HK_LAUNCH_CHECK(ctx);
+    k_fixed_base_mul<F, Fr><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(tbl, d_scalars, mont ? 1 : 0,
+                                                                       reinterpret_cast<Affine<F>*>(d_out_affine), n);
+    HK_LAUNCH_CHECK(ctx);
+}
+template void fixed_base_mul<Bls12381, 1>(hk_ctx*, const void*, const Scalar256*, size_t, bool, void*);
+template void fixed_base_mul<Bls12381, 2>(hk_ctx*, const void*, const Scalar256*, size_t, bool, void*);
+template void fixed_base_mul<Bn254, 1>(hk_ctx*, const void*, const Scalar256*, size_t, bool, void*);
+template void fixed_base_mul<Bn254, 2>(hk_ctx*, const void*, const Scalar256*, size_t, bool, void*);
+
+static BaseSet& get_bases(hk_ctx* ctx, uint64_t h, int group) {
+    auto it = ctx->bases.find(h);
+    HK_REQUIRE(it != ctx->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
+    HK_REQUIRE(it->second->group == group, HK_ERR_INVALID, "base set is in the wrong group");
+    return *it->second;
+}
+
+template <class Curve>
+std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d) {
+    using Fq = typename Curve::Fq;
+    using Fq2 = typename Curve::Fq2;
+    const size_t P1 = sizeof(Affine<Fq>), P2 = sizeof(Affine<Fq2>);
+    auto pk = std::make_shared<PkDev>();
+    HK_REQUIRE(d.num_stages >= 1 && d.num_stages <= 8, HK_ERR_INVALID, "pk: num_stages must be 1..8");
+    auto rit = ctx->r1cs.find(d.r1cs);
+    HK_REQUIRE(rit != ctx->r1cs.end(), HK_ERR_HANDLE, "pk: unknown r1cs handle");
+    pk->r1cs = rit->second;
+    pk->num_stages = d.num_stages;
+    const size_t l = pk->r1cs->l, nw = pk->r1cs->nw, m = l + nw;
+    pk->m = m;
+    const size_t N = size_t(1) << pk->r1cs->log_n;
+    BaseSet& a_g = get_bases(ctx, d.a_g, 1);
+    BaseSet& b_g = get_bases(ctx, d.b_g, 1);
+    BaseSet& b_h = get_bases(ctx, d.b_h, 2);
+    BaseSet& h_g = get_bases(ctx, d.h_g, 1);
+    BaseSet& deltas = get_bases(ctx, d.deltas_g, 1);
+    HK_REQUIRE(a_g.n == m && b_g.n == m && b_h.n == m, HK_ERR_LENGTH, "pk: a_g/b_g/b_h must have one point per variable");
+    HK_REQUIRE(h_g.n == N - 1, HK_ERR_LENGTH, "pk: h_g must have N-1 points (prover.rs:128)");
+    HK_REQUIRE(deltas.n == d.num_stages, HK_ERR_LENGTH, "pk: deltas_g must have num_stages points");
+    HK_REQUIRE(m >= 1, HK_ERR_INVALID, "pk: no variables");
+    for (uint32_t i = 0; i <= d.num_stages; i++) pk->stage_start.push_back(d.stage_start[i]);
+    HK_REQUIRE(pk->stage_start[0] == 0 && pk->stage_start[d.num_stages] <= nw, HK_ERR_INVALID,
+               "pk: stage ranges must start at 0 and stay within the witness");
+    cudaStream_t st = ctx->stream;
+    auto cp = [&](void* dst, const void* src, size_t bytes, cudaMemcpyKind k) {
+        if (bytes) HK_CUDA(cudaMemcpyAsync(dst, src, bytes, k, st));
+    };
+    // [q[1..m-1], q[0], vk_param, delta]
+    char* a_ext = (char*)pk->a_ext.ensure((m + 2) * P1);
+    cp(a_ext, (char*)a_g.d + P1, (m - 1) * P1, cudaMemcpyDeviceToDevice);
+    cp(a_ext + (m - 1) * P1, a_g.d, P1, cudaMemcpyDeviceToDevice);
+    cp(a_ext + m * P1, d.alpha_g, P1, cudaMemcpyHostToDevice);
+    cp(a_ext + (m + 1) * P1, (char*)deltas.d + (d.num_stages - 1) * P1, P1, cudaMemcpyDeviceToDevice);
+    char* b1_ext = (char*)pk->b1_ext.ensure((m + 2) * P1);
+    cp(b1_ext, (char*)b_g.d + P1, (m - 1) * P1, cudaMemcpyDeviceToDevice);
+    cp(b1_ext + (m - 1) * P1, b_g.d, P1, cudaMemcpyDeviceToDevice);
+    cp(b1_ext + m * P1, d.beta_g, P1, cudaMemcpyHostToDevice);
+    cp(b1_ext + (m + 1) * P1, (char*)deltas.d + (d.num_stages - 1) * P1, P1, cudaMemcpyDeviceToDevice);
+    char* b2_ext = (char*)pk->b2_ext.ensure((m + 2) * P2);
+    cp(b2_ext, (char*)b_h.d + P2, (m - 1) * P2, cudaMemcpyDeviceToDevice);
+    cp(b2_ext + (m - 1) * P2, b_h.d, P2, cudaMemcpyDeviceToDevice);
+    cp(b2_ext + m * P2, d.beta_h, P2, cudaMemcpyHostToDevice);
+    cp(b2_ext + (m + 1) * P2, d.last_delta_h, P2, cudaMemcpyHostToDevice);
+    // per-stage committer keys: [ck[stage].., delta_last]; the last stage's doubles as L' with the
+    // deltas appended: [ck_last.., delta_last, deltas_g[0..ns-2]]
+    for (uint32_t sidx = 0; sidx < d.num_stages; sidx++) {
+        BaseSet& ck = get_bases(ctx, d.ck[sidx], 1);
+        size_t want = pk->stage_start[sidx + 1] - pk->stage_start[sidx];
+        HK_REQUIRE(ck.n == want, HK_ERR_LENGTH, "pk: ck[stage] length must equal the stage's witness count");
+        pk->ck_ext.emplace_back(new DevBuf());
+        size_t extra = (sidx + 1 == d.num_stages) ? d.num_stages : 1;
+        char* e = (char*)pk->ck_ext.back()->ensure((ck.n + extra) * P1);
+        cp(e, ck.d, ck.n * P1, cudaMemcpyDeviceToDevice);
+        cp(e + ck.n * P1, (char*)deltas.d + (d.num_stages - 1) * P1, P1, cudaMemcpyDeviceToDevice);
+        if (extra > 1) cp(e + (ck.n + 1) * P1, deltas.d, (d.num_stages - 1) * P1, cudaMemcpyDeviceToDevice);
+    }
+    pk->h_g = h_g.d;
+    pk->h_g_handle = d.h_g;
+    HK_CUDA(cudaStreamSynchronize(st));
+    return pk;
+}
+template std::shared_ptr<PkDev> pk_create<Bls12381>(hk_ctx*, const hk_pk_desc&);
+template std::shared_ptr<PkDev> pk_create<Bn254>(hk_ctx*, const hk_pk_desc&);
+
+template <class Curve>
+void commit_run(hk_ctx* ctx, PkDev& pk, uint32_t stage, const uint64_t* d_z, const uint64_t* d_kappa,
+                void* d_out_affine, uint8_t* d_inf) {
+    using Fr = typename Curve::Fr;
+    using Fq = typename Curve::Fq;
+    HK_REQUIRE(stage < pk.num_stages, HK_ERR_INVALID, "commit: no such stage (\"no more values left in committing key\")");
+    const size_t l = pk.r1cs->l;
+    const size_t nw = pk.stage_start[stage + 1] - pk.stage_start[stage];
+    const Fr* w = reinterpret_cast<const Fr*>(d_z) + l + pk.stage_start[stage];
+    Fr* sc = ctx->ws_io[0].as<Fr>(nw + 1);
+    k_build_commit_scalars<Fr><<<ceil_div(nw + 1, 256), 256, 0, ctx->stream>>>(w, nw, reinterpret_cast<const Fr*>(d_kappa), sc);
+    HK_LAUNCH_CHECK(ctx);
+    Jacobian<Fq>* jac = ctx->ws_out.as<Jacobian<Fq>>(8);
+    msm_run<Curve, 1>(ctx, pk.ck_ext[stage]->p, nw + 1, reinterpret_cast<const Scalar256*>(sc), 1, true, jac);
+    jac_to_affine<Curve, 1>(ctx, jac, d_out_affine, d_inf, 1);
+}
+template void commit_run<Bls12381>(hk_ctx*, PkDev&, uint32_t, const uint64_t*, const uint64_t*, void*, uint8_t*);
+template void commit_run<Bn254>(hk_ctx*, PkDev&, uint32_t, const uint64_t*, const uint64_t*, void*, uint8_t*);
+
+template <class Curve>
+void prove_run(hk_ctx* ctx, PkDev& pk, const uint64_t* d_z_v, const uint64_t* d_r, const uint64_t* d_s,
+               const uint64_t* d_kappas, void* d_outA, void* d_outB, void* d_outC, uint8_t* d_inf) {
+    using Fr = typename Curve::Fr;
+    using Fq = typename Curve::Fq;
+    using Fq2 = typename Curve::Fq2;
+    const Fr* z = reinterpret_cast<const Fr*>(d_z_v);
+    const Fr* r = reinterpret_cast<const Fr*>(d_r);
+    const Fr* s = reinterpret_cast<const Fr*>(d_s);
+    const size_t m = pk.m, l = pk.r1cs->l;
+    const uint32_t log_n = pk.r1cs->log_n;
+    const size_t N = size_t(1) << log_n;
+    const uint32_t ns = pk.num_stages;
+    cudaStream_t st = ctx->stream;
+    Jacobian<Fq>* jac = ctx->ws_out.as<Jacobian<Fq>>(8);          // A, B1, L', H
+    Jacobian<Fq2>* jacB2 = reinterpret_cast<Jacobian<Fq2>*>(jac + 4);
+    // A, B1, B2: shared canonical scalar vector, last entry r then s
+    Scalar256* S = ctx->ws_io[0].as<Scalar256>(m + 2);
+    k_build_abc_scalars<Fr><<<ceil_div(m + 2, 256), 256, 0, st>>>(z, m, r, S);
+    HK_LAUNCH_CHECK(ctx);
+    msm_run<Curve, 1>(ctx, pk.a_ext.p, m + 2, S, 1, false, jac + 0);
+    k_patch_scalar<Fr><<<1, 1, 0, st>>>(s, S + m + 1);
+    HK_LAUNCH_CHECK(ctx);
+    msm_run<Curve, 1>(ctx, pk.b1_ext.p, m + 2, S, 1, false, jac + 1);
+    msm_run<Curve, 2>(ctx, pk.b2_ext.p, m + 2, S, 1, false, jacB2);
+    // L'
+    const size_t nl = pk.stage_start[ns] - pk.stage_start[ns - 1];
+    Fr* Ls = ctx->ws_io[1].as<Fr>(nl + ns);
+    k_build_l_scalars<Fr><<<ceil_div(nl + ns, 256), 256, 0, st>>>(z + l + pk.stage_start[ns - 1], nl, r, s,
+                                                                 reinterpret_cast<const Fr*>(d_kappas), ns - 1, Ls);
+    HK_LAUNCH_CHECK(ctx);
+    msm_run<Curve, 1>(ctx, pk.ck_ext[ns - 1]->p, nl + ns, reinterpret_cast<const Scalar256*>(Ls), 1, true, jac + 2);
+    // h and H
+    uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N);
+    uint64_t* h = ctx->ws_qap[1].as<uint64_t>(4 * N);
+    r1cs_evals<Curve>(ctx, *pk.r1cs, d_z_v, abc);
+    qap_h_from_evals<Curve>(ctx, log_n, abc, h);
+    msm_run<Curve, 1>(ctx, pk.h_g, N - 1, reinterpret_cast<const Scalar256*>(h), 1, true, jac + 3);
+    k_prove_finish<Curve><<<1, 96, 0, st>>>(jac, jacB2, r, s, reinterpret_cast<Affine<Fq>*>(d_outA),
+                                            reinterpret_cast<Affine<Fq2>*>(d_outB),
+                                            reinterpret_cast<Affine<Fq>*>(d_outC), d_inf);
+    HK_LAUNCH_CHECK(ctx);
+}
+template void prove_run<Bls12381>(hk_ctx*, PkDev&, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
+                                  void*, void*, void*, uint8_t*);
+template void prove_run<Bn254>(hk_ctx*, PkDev&, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
+                               void*, void*, void*, uint8_t*);
+
+}  // namespace hk

@@ -1,0 +1,198 @@
+/*
+ * hekaton_b200.h -- C ABI of the B200-native (sm_100a) backend for Hekaton's per-subcircuit
+ * CP-Groth16 hot path.  This is the drop-in boundary: the entry points are exactly what a
+ * Rust `-sys` crate for cp-groth16 would bind (INTEGRATION.md shows the binding).
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *   hk_msm_g1 / hk_msm_g2        ark-ec `VariableBaseMSM::{msm, msm_unchecked, msm_bigint}` as
+ *                                called at cp-groth16/src/committer.rs:89,113 and
+ *                                cp-groth16/src/prover.rs:117,129,168 (via calculate_coeff :158-171)
+ *   hk_ntt                       ark-poly `EvaluationDomain::{fft_in_place, ifft_in_place}` on a
+ *                                Radix2EvaluationDomain and its `get_coset(F::GENERATOR)`, reached
+ *                                through `QAP::witness_map` at cp-groth16/src/prover.rs:123
+ *   hk_qap_h, hk_r1cs_*,         ark-groth16 `LibsnarkReduction::witness_map_from_matrices`
+ *   hk_qap_witness_map           (re-exported at cp-groth16/src/lib.rs:9-10; call prover.rs:123)
+ *   hk_bases_upload_*            the proving-key vectors of cp-groth16/src/data_structures.rs:66-114
+ *                                (a_g, b_g, b_h, h_g, ck.deltas_abc_g, deltas_g), uploaded once
+ *   hk_pk_*, hk_commit, hk_prove the fused per-subcircuit path: CommitmentBuilder::commit
+ *                                (committer.rs:55-98) and CommitmentBuilder::prove ->
+ *                                prove_last_stage (committer.rs:100-122, prover.rs:53-156)
+ *
+ * Conventions
+ *   - All functions return int32_t: 0 = HK_OK, negative = error (hk_last_error_string()).
+ *     Nothing throws or aborts across the boundary.  There is NO CPU fallback: without a
+ *     usable sm_100 device hk_ctx_create fails.
+ *   - Field elements are little-endian arrays of u64 limbs in MONTGOMERY form with
+ *     R = 2^(64*LIMBS) -- the in-memory layout of ark-ff 0.4 `Fp<MontBackend<_,N>,N>`:
+ *     Fr: 4 limbs (both curves).  Fq: 6 limbs (BLS12-381) / 4 limbs (BN254).
+ *     Fq2 = c0 || c1.  Scalars passed with HK_SCALAR_BIGINT are canonical integers
+ *     (`BigInt<4>`, what `into_bigint()` yields; prover.rs:78-82).
+ *   - Affine points: x || y (G2: x.c0 x.c1 y.c0 y.c1) plus an optional byte-per-point
+ *     infinity array (arkworks `Affine{x,y,infinity}` is not repr(C): the shim copies
+ *     fields, never transmutes).
+ *   - MSM results are Jacobian (X, Y, Z), x = X/Z^2, y = Y/Z^3, identity Z = 0 -- the
+ *     representation of ark-ec `short_weierstrass::Projective`.  Any representative of the
+ *     group element may be returned; equality with the reference is after into_affine().
+ *   - `memspace`: HK_HOST = pointers are host memory (copies are part of the call),
+ *     HK_DEVICE = pointers are device memory on the context's GPU (no copies).
+ *   - A context is bound to one GPU and one CUDA stream and is not thread-safe; use one
+ *     context per host thread (the reference runs several proofs concurrently on separate
+ *     threads, mpi-snark/src/bin/node.rs:773-793).  Calls with HK_HOST outputs
+ *     synchronise the stream before returning; HK_DEVICE calls are asynchronous.
+ */
+#ifndef HEKATON_B200_H
+#define HEKATON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hk_ctx hk_ctx;
+
+enum { HK_CURVE_BLS12_381 = 0, HK_CURVE_BN254 = 1 };
+enum { HK_HOST = 0, HK_DEVICE = 1 };
+enum { HK_SCALAR_BIGINT = 0, HK_SCALAR_MONT = 1 };
+enum { HK_NTT_FORWARD = 0, HK_NTT_INVERSE = 1 };
+enum { HK_DOMAIN_PLAIN = 0, HK_DOMAIN_COSET_GENERATOR = 1 };
+
+enum {
+    HK_OK = 0,
+    HK_ERR_INVALID = -1,     /* bad argument */
+    HK_ERR_CUDA = -2,        /* CUDA runtime error (text in hk_last_error_string) */
+    HK_ERR_NOMEM = -3,
+    HK_ERR_LENGTH = -4,      /* length mismatch where the reference returns Err (msm) */
+    HK_ERR_HANDLE = -5,      /* unknown handle */
+    HK_ERR_UNSUPPORTED = -6, /* e.g. log_n above the field's two-adicity */
+    HK_ERR_NO_DEVICE = -7    /* no sm_100 GPU: there is no CPU fallback */
+};
+
+/* Field ids for the element-wise test entry point. */
+enum { HK_FIELD_FR = 0, HK_FIELD_FQ = 1, HK_FIELD_FQ2 = 2 };
+enum { HK_FOP_MUL = 0, HK_FOP_ADD = 1, HK_FOP_SUB = 2, HK_FOP_INV = 3, HK_FOP_TO_MONT = 4, HK_FOP_FROM_MONT = 5 };
+
+/* ---- context ---------------------------------------------------------------------- */
+/* `stream`: a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create one. */
+int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx** out);
+int32_t hk_ctx_destroy(hk_ctx* ctx);
+int32_t hk_ctx_sync(hk_ctx* ctx);
+const char* hk_last_error_string(hk_ctx* ctx);
+/* Limb counts for this context's curve (fq_limbs64 = 6 or 4; fr_limbs64 = 4). */
+int32_t hk_curve_info(hk_ctx* ctx, uint32_t* fq_limbs64, uint32_t* fr_limbs64, uint32_t* fr_bits,
+                      uint32_t* two_adicity);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t hk_launch_count(hk_ctx* ctx);
+
+/* ---- bases (proving-key vectors; data_structures.rs:66-114) ------------------------- */
+int32_t hk_bases_upload_g1(hk_ctx* ctx, const void* affine_xy_mont, const uint8_t* infinity, size_t n,
+                           uint32_t memspace, uint64_t* handle);
+int32_t hk_bases_upload_g2(hk_ctx* ctx, const void* affine_xy_mont, const uint8_t* infinity, size_t n,
+                           uint32_t memspace, uint64_t* handle);
+int32_t hk_bases_free(hk_ctx* ctx, uint64_t handle);
+int32_t hk_bases_len(hk_ctx* ctx, uint64_t handle, size_t* n);
+/* Copy points back (affine, Montgomery; infinity as (0,0)); out holds n points. */
+int32_t hk_bases_download(hk_ctx* ctx, uint64_t handle, size_t offset, size_t n, void* out);
+/* Setup helper (generator.rs:128-196 `FixedBase::msm`, restricted to what a synthetic CRS
+ * needs): out[i] = scalars[i] * G for an affine generator G; creates a base set. */
+int32_t hk_bases_from_scalars_g1(hk_ctx* ctx, const void* gen_affine_mont, const uint64_t* scalars,
+                                 size_t n, uint32_t scalar_repr, uint32_t memspace, uint64_t* handle);
+int32_t hk_bases_from_scalars_g2(hk_ctx* ctx, const void* gen_affine_mont, const uint64_t* scalars,
+                                 size_t n, uint32_t scalar_repr, uint32_t memspace, uint64_t* handle);
+
+/* ---- MSM (VariableBaseMSM) ----------------------------------------------------------
+ * result = sum_{i<n} scalars[i] * bases[base_offset + i].
+ * `n` is the number of scalars supplied.  hk_msm_* follow `msm_unchecked`/`msm_bigint`:
+ * if fewer than n bases remain after base_offset the sum silently covers the shorter
+ * length (committer.rs:110-113 relies on this).  hk_msm_*_checked follows `msm`: it
+ * returns HK_ERR_LENGTH unless exactly n_bases_expected == n (committer.rs:89).
+ * n == 0 -> identity (prover.rs:117 unwrap_or(zero)).  out: 3 field elements (Jacobian). */
+int32_t hk_msm_g1(hk_ctx* ctx, uint64_t bases, size_t base_offset, const uint64_t* scalars, size_t n,
+                  uint32_t scalar_repr, uint32_t memspace, void* out_jacobian);
+int32_t hk_msm_g2(hk_ctx* ctx, uint64_t bases, size_t base_offset, const uint64_t* scalars, size_t n,
+                  uint32_t scalar_repr, uint32_t memspace, void* out_jacobian);
+int32_t hk_msm_g1_checked(hk_ctx* ctx, uint64_t bases, size_t base_offset, size_t n_bases_expected,
+                          const uint64_t* scalars, size_t n, uint32_t scalar_repr, uint32_t memspace,
+                          void* out_jacobian);
+/* K scalar vectors against the same base range (same-shape subcircuits share a key). */
+int32_t hk_msm_g1_batch(hk_ctx* ctx, uint64_t bases, size_t base_offset, const uint64_t* scalars, size_t n,
+                        size_t K, uint32_t scalar_repr, uint32_t memspace, void* out_jacobian);
+int32_t hk_msm_g2_batch(hk_ctx* ctx, uint64_t bases, size_t base_offset, const uint64_t* scalars, size_t n,
+                        size_t K, uint32_t scalar_repr, uint32_t memspace, void* out_jacobian);
+
+/* Jacobian -> affine (CurveGroup::into_affine; prover.rs:152-154).  in: n*3 elements,
+ * out: n*2 elements (Montgomery), inf_out: n bytes (may be NULL). Host pointers. */
+int32_t hk_g1_into_affine(hk_ctx* ctx, const void* jac, size_t n, void* out_xy, uint8_t* inf_out);
+int32_t hk_g2_into_affine(hk_ctx* ctx, const void* jac, size_t n, void* out_xy, uint8_t* inf_out);
+
+/* ---- NTT (Radix2EvaluationDomain) ---------------------------------------------------
+ * In-place, natural order in and out, size 2^log_n, Montgomery Fr.
+ * dir = HK_NTT_FORWARD:  fft_in_place  (on a coset: x_i *= g^i first)
+ * dir = HK_NTT_INVERSE:  ifft_in_place (includes 1/N; on a coset: then x_i *= g^-i)
+ * domain = HK_DOMAIN_COSET_GENERATOR uses offset F::GENERATOR (7 / 5). */
+int32_t hk_ntt(hk_ctx* ctx, uint64_t* inout, uint32_t log_n, uint32_t dir, uint32_t domain, uint32_t memspace);
+int32_t hk_ntt_batch(hk_ctx* ctx, uint64_t* inout, uint32_t log_n, size_t K, uint32_t dir, uint32_t domain,
+                     uint32_t memspace);
+
+/* ---- R1CS -> QAP witness map (LibsnarkReduction) ------------------------------------
+ * hk_qap_h: a, b, c are the length-2^log_n evaluation vectors (zero padded;
+ * a[n..n+l] = instance assignment); h receives all 2^log_n coefficients. */
+int32_t hk_qap_h(hk_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, uint32_t log_n,
+                 uint32_t memspace, uint64_t* h);
+/* Resident constraint matrices (CSR over columns [instance || witness]); coefficients
+ * Montgomery Fr.  row_ptr has num_constraints+1 entries per matrix. */
+int32_t hk_r1cs_upload(hk_ctx* ctx, size_t num_constraints, size_t num_instance, size_t num_witness,
+                       const uint32_t* a_row_ptr, const uint32_t* a_col, const uint64_t* a_val,
+                       const uint32_t* b_row_ptr, const uint32_t* b_col, const uint64_t* b_val,
+                       const uint32_t* c_row_ptr, const uint32_t* c_col, const uint64_t* c_val,
+                       uint64_t* handle);
+int32_t hk_r1cs_free(hk_ctx* ctx, uint64_t handle);
+/* witness_map(cs): z = full assignment (instance || witness), Montgomery Fr, length
+ * num_instance + num_witness; h receives 2^log_n coefficients, log_n = ceil_log2(n + l). */
+int32_t hk_qap_witness_map(hk_ctx* ctx, uint64_t r1cs, const uint64_t* z, uint32_t memspace, uint64_t* h);
+
+/* ---- fused per-subcircuit path ------------------------------------------------------ */
+typedef struct hk_pk_desc {
+    uint64_t a_g, b_g, h_g;   /* G1 base-set handles (data_structures.rs:71-77) */
+    uint64_t b_h;             /* G2 base-set handle */
+    uint64_t ck[8];           /* ck.deltas_abc_g[stage], G1 handles */
+    uint32_t num_stages;
+    uint64_t deltas_g;        /* G1 handle, num_stages points */
+    const void* alpha_g;      /* vk.alpha_g  (G1 affine, host) */
+    const void* beta_g;       /* G1 affine, host */
+    const void* beta_h;       /* vk.beta_h   (G2 affine, host) */
+    const void* last_delta_h; /* vk.deltas_h.last() (G2 affine, host) */
+    uint64_t r1cs;            /* hk_r1cs_upload handle */
+    uint32_t stage_start[9];  /* witness index ranges: stage i = [stage_start[i], stage_start[i+1]) */
+} hk_pk_desc;
+
+int32_t hk_pk_create(hk_ctx* ctx, const hk_pk_desc* desc, uint64_t* pk_handle);
+int32_t hk_pk_free(hk_ctx* ctx, uint64_t pk_handle);
+/* committer.rs:85-91: com = MSM(ck[stage], w_stage) + kappa * last_delta_g  -> affine.
+ * z: full assignment so far (Montgomery Fr; at least instance + stage witnesses).
+ * kappa: Montgomery Fr.  out: G1 affine (x||y Montgomery), inf flag. */
+int32_t hk_commit(hk_ctx* ctx, uint64_t pk, uint32_t stage, const uint64_t* z, const uint64_t* kappa,
+                  uint32_t memspace, void* com_affine, uint8_t* com_inf);
+/* prover.rs:53-156 + committer.rs:106-114.  z: full assignment (Montgomery Fr),
+ * r, s: Montgomery Fr, kappas: num_stages-1 Montgomery Fr.
+ * out: A (G1 affine), B (G2 affine), C (G1 affine), each x||y Montgomery; inf[3]. */
+int32_t hk_prove(hk_ctx* ctx, uint64_t pk, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                 const uint64_t* kappas, uint32_t memspace, void* a_affine, void* b_affine, void* c_affine,
+                 uint8_t* inf);
+
+/* ---- test / measurement hooks ------------------------------------------------------- */
+/* Element-wise field op on n elements (host pointers): out[i] = a[i] (op) b[i]. */
+int32_t hk_field_op(hk_ctx* ctx, uint32_t field, uint32_t op, const uint64_t* a, const uint64_t* b,
+                    uint64_t* out, size_t n);
+/* Dependent-chain multiply throughput probe: `iters` Montgomery multiplies per thread on
+ * `threads` threads; returns elapsed milliseconds (CUDA events on the context stream). */
+int32_t hk_bench_field_mul(hk_ctx* ctx, uint32_t field, uint32_t threads, uint32_t iters, float* ms);
+/* Raw IMAD.WIDE.U32 issue-rate probe (the MSM roofline denominator): returns wide
+ * multiply-accumulates per second. */
+int32_t hk_bench_imad_wide(hk_ctx* ctx, uint32_t iters, double* macs_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEKATON_B200_H */

@@ -1,0 +1,46 @@
+"""GPU parity for the fused path: setup -> commit -> prove reads like the reference's
+poly_commit_test (cp-groth16/src/lib.rs:139-180, 273-313); the acceptance check is stronger than
+verify_proof: every output equals the oracle's restated prover AND the trapdoor known answer."""
+import pytest
+
+from hekaton_system_b200 import cp_groth16 as host
+from oracle import cpgroth16 as og
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("ncons,stage0", [(5, 2), (60, 7), (300, 40)])
+def test_two_stage_commit_prove(ctx, ncons, stage0):
+    cv = ctx.curve
+    circ = og.synthetic_circuit(cv.name, ncons, stage0_witnesses=stage0, seed=ncons)
+    td = og.sample_trapdoor(cv.name, 2, ncons + 1)
+    opk = og.generate_parameters(cv.name, circ, td)
+    pk = host.ProvingKey.from_key(ctx, opk, circ)
+    cb = host.CommitmentBuilder(host.StagedAssignment.from_circuit(circ, cv), pk)
+    kappa, r_, s_ = 0x1111222233334444555566667777, cv.r - 5, 0x9999aaaabbbbccccdddd
+    com, rand = cb.commit(kappa=kappa)
+    assert rand == kappa
+    assert com == og.commit(opk, circ, 0, kappa)
+    proof = cb.prove([com], [rand], r=r_, s=s_)
+    A, Bp, C = og.prove(opk, circ, r_, s_, [kappa])
+    assert (proof.a, proof.b, proof.c) == (A, Bp, C)
+    exp = og.trapdoor_expected(opk, circ, td, r_, s_, [kappa])
+    assert (proof.a, proof.b, proof.c, com) == (exp["A"], exp["B"], exp["C"], exp["D"][0])
+    assert proof.ds == [com]
+    with pytest.raises(IndexError):
+        cb.commit(kappa=1)
+        cb.commit(kappa=1)
+
+
+def test_single_stage_and_zero_randomness(ctx):
+    cv = ctx.curve
+    circ = og.synthetic_circuit(cv.name, 40, stage0_witnesses=0, seed=8)
+    circ.stage_ranges = [(0, len(circ.witness))]
+    td = og.sample_trapdoor(cv.name, 1, 9)
+    opk = og.generate_parameters(cv.name, circ, td)
+    pk = host.ProvingKey.from_key(ctx, opk, circ)
+    for r_, s_ in ((0, 0), (5, 0), (0, 7), (123456789, 987654321)):   # prove_last_stage_without_zk / r == 0 branch
+        cb = host.CommitmentBuilder(host.StagedAssignment.from_circuit(circ, cv), pk)
+        proof = cb.prove([], [], r=r_, s=s_)
+        exp = og.trapdoor_expected(opk, circ, td, r_, s_, [])
+        assert (proof.a, proof.b, proof.c) == (exp["A"], exp["B"], exp["C"]), (r_, s_)

@@ -1,0 +1,430 @@
+#!/usr/bin/env python3
+"""Generator for the sm_100a Montgomery field kernels (hekaton_system_b200/csrc/field_gen.cuh).
+
+Why generated: on sm_100a ptxas lowers `mad.lo.cc/madc.hi.cc` to IMAD(.HI) + IADD3.X
+(4 SASS per 32x32 MAC) but fuses `mul.wide.u32` + `add.cc.u64/addc.cc.u64` into ONE
+`IMAD.WIDE.U32.X Rd, Pc, Ra, Rb, Rd, Pc` (multiply, 64-bit accumulate, carry in, carry
+out).  So field elements are kept as 64-bit lanes and the Montgomery product is a set
+of carry chains over two families of 64-bit lanes (even / odd 32-bit column alignment).
+Each operation is emitted as a single fully unrolled PTX block with the modulus as
+immediates; the same instruction list is executed by the simulator below
+(tests/test_field_gen.py) against Python big integers, so the arithmetic is verified
+without a GPU.
+
+Algorithm (mont_mul, N 32-bit limbs, N even, p < 2^(32N-1)):
+  lanes L[c] = 64-bit accumulator covering absolute 32-bit columns (c, c+1).
+  row i (0..N-1):
+    X_i : L[i+j]  += a_j*b_i   j even (first product also adds x_i, the high half of
+                                L[i-1] left over from the previous row); carry -> L[i+N]
+    Y_i : L[i+j]  += a_j*b_i   j odd ; no carry out (total < 2^(32(i+N+1)))
+    m_i  = lo32(L[i]) * (-p^-1 mod 2^32)
+    X'_i: L[i+j]  += m_i*p_j   j even; carry -> L[i+N]
+    Y'_i: L[i+j]  += m_i*p_j   j odd
+    now lo32(L[i]) == 0 ;  x_{i+1} = hi32(L[i])
+  result = (columns N..2N-1) = even family + odd family, then one conditional subtract.
+Cost: 2N^2 + N wide multiplies (+ N low multiplies for m_i).
+"""
+import argparse
+import os
+import random
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+
+M32 = (1 << 32) - 1
+M64 = (1 << 64) - 1
+
+
+class Prog:
+    """Tiny PTX-subset program builder + simulator."""
+
+    def __init__(self):
+        self.ins = []       # (op, dst, srcs)
+        self.regs64 = []
+        self.regs32 = []
+        self.preds = []
+        self._n = 0
+
+    def r64(self, hint="q"):
+        self._n += 1
+        name = f"{hint}{self._n}"
+        self.regs64.append(name)
+        return name
+
+    def r32(self, hint="w"):
+        self._n += 1
+        name = f"{hint}{self._n}"
+        self.regs32.append(name)
+        return name
+
+    def pred(self):
+        self._n += 1
+        name = f"p{self._n}"
+        self.preds.append(name)
+        return name
+
+    def emit(self, op, dst, *srcs):
+        self.ins.append((op, dst, srcs))
+
+    # ---------------- simulation ----------------
+    def run(self, env):
+        """env: dict name -> int for inputs.  Returns env after execution."""
+        R = dict(env)
+        cf = 0
+
+        def val(s):
+            if isinstance(s, int):
+                return s
+            return R[s]
+
+        for op, dst, srcs in self.ins:
+            if op == "mul.wide.u32":
+                R[dst] = (val(srcs[0]) & M32) * (val(srcs[1]) & M32)
+            elif op == "mad.wide.u32":
+                v = (val(srcs[0]) & M32) * (val(srcs[1]) & M32) + val(srcs[2])
+                assert v <= M64, "mad.wide overflow (would silently wrap)"
+                R[dst] = v
+            elif op == "mul.lo.u32":
+                R[dst] = (val(srcs[0]) * val(srcs[1])) & M32
+            elif op in ("add.cc.u64", "addc.cc.u64", "addc.u64", "add.u64"):
+                v = val(srcs[0]) + val(srcs[1]) + (cf if op.startswith("addc") else 0)
+                R[dst] = v & M64
+                if ".cc" in op:
+                    cf = v >> 64
+                elif op == "addc.u64":
+                    pass
+            elif op in ("sub.cc.u64", "subc.cc.u64", "subc.u64"):
+                v = val(srcs[0]) - val(srcs[1]) - (cf if op.startswith("subc") else 0)
+                R[dst] = v & M64
+                if ".cc" in op:
+                    cf = 1 if v < 0 else 0
+            elif op == "subc.u32":
+                v = val(srcs[0]) - val(srcs[1]) - cf
+                R[dst] = v & M32
+            elif op == "unpack":          # mov.b64 {lo,hi}, src
+                lo, hi = dst
+                v = val(srcs[0])
+                R[lo] = v & M32
+                R[hi] = v >> 32
+            elif op == "pack":            # mov.b64 dst, {lo,hi}
+                R[dst] = (val(srcs[0]) & M32) | ((val(srcs[1]) & M32) << 32)
+            elif op == "mov.u64":
+                R[dst] = val(srcs[0])
+            elif op == "setp.ne.u32":
+                R[dst] = 1 if val(srcs[0]) != val(srcs[1]) else 0
+            elif op == "selp.b64":
+                R[dst] = val(srcs[0]) if R[srcs[2]] else val(srcs[1])
+            elif op == "and.b64":
+                R[dst] = val(srcs[0]) & val(srcs[1])
+            elif op == "assert_nc":
+                assert cf == 0, "dropped a non-zero carry"
+            elif op == "assert_lo0":
+                assert val(srcs[0]) & M32 == 0
+            else:
+                raise ValueError(op)
+        return R
+
+    # ---------------- PTX text ----------------
+    def ptx(self, operand_map):
+        """operand_map: name -> '%k' for asm operands.  Returns list of PTX lines."""
+        def o(s):
+            if isinstance(s, int):
+                return hex(s)
+            return operand_map.get(s, s)
+
+        lines = []
+        r64 = [r for r in self.regs64 if r not in operand_map]
+        r32 = [r for r in self.regs32 if r not in operand_map]
+        if r64:
+            lines.append(".reg .u64 " + ", ".join(r64) + ";")
+        if r32:
+            lines.append(".reg .u32 " + ", ".join(r32) + ";")
+        if self.preds:
+            lines.append(".reg .pred " + ", ".join(self.preds) + ";")
+        for op, dst, srcs in self.ins:
+            if op in ("assert_nc", "assert_lo0"):
+                continue
+            if op == "unpack":
+                lines.append(f"mov.b64 {{{o(dst[0])}, {o(dst[1])}}}, {o(srcs[0])};")
+            elif op == "pack":
+                lines.append(f"mov.b64 {o(dst)}, {{{o(srcs[0])}, {o(srcs[1])}}};")
+            else:
+                lines.append(f"{op} {o(dst)}, " + ", ".join(o(s) for s in srcs) + ";")
+        return lines
+
+
+def limbs32(x, n):
+    return [(x >> (32 * i)) & M32 for i in range(n)]
+
+
+def lanes64(x, n2):
+    return [(x >> (64 * i)) & M64 for i in range(n2)]
+
+
+class FieldGen:
+    def __init__(self, name, p):
+        self.name = name
+        self.p = p
+        self.N = ((p.bit_length() + 63) // 64) * 2        # 32-bit limbs, even
+        self.N2 = self.N // 2
+        assert p.bit_length() <= 32 * self.N - 1, "need a spare top bit"
+        self.R = 1 << (32 * self.N)
+        self.m32 = (-pow(p, -1, 1 << 32)) % (1 << 32)
+        self.pl = limbs32(p, self.N)
+        self.p64 = lanes64(p, self.N2)
+
+    # -- shared tail: r (N2 lanes, < 2p) -> r mod p into output names
+    def _final_sub(self, P, lanes, outs):
+        t = [P.r64("t") for _ in range(self.N2)]
+        for k in range(self.N2):
+            P.emit("sub.cc.u64" if k == 0 else "subc.cc.u64", t[k], lanes[k], self.p64[k])
+        bw = P.r32("bw")
+        P.emit("subc.u32", bw, 0, 0)           # 0xffffffff if r < p (borrow), else 0
+        pr = P.pred()
+        P.emit("setp.ne.u32", pr, bw, 0)
+        for k in range(self.N2):
+            P.emit("selp.b64", outs[k], lanes[k], t[k], pr)
+
+    def gen_mul(self):
+        N, N2 = self.N, self.N2
+        P = Prog()
+        outs = [f"r{k}" for k in range(N2)]
+        ain = [f"a{k}" for k in range(N2)]
+        bin_ = [f"b{k}" for k in range(N2)]
+        a = []
+        b = []
+        for k in range(N2):
+            lo, hi = P.r32("al"), P.r32("ah")
+            P.emit("unpack", (lo, hi), ain[k])
+            a += [lo, hi]
+        for k in range(N2):
+            lo, hi = P.r32("bl"), P.r32("bh")
+            P.emit("unpack", (lo, hi), bin_[k])
+            b += [lo, hi]
+        L = {}
+        x = None            # 32-bit register: hi32 of the retired lane
+
+        def chain(cols, prods, carry_lane, first_addend=None):
+            """prods: list of (u32 reg/imm, u32 reg/imm) per lane col."""
+            carrying = False
+            for idx, (c, (u, v)) in enumerate(zip(cols, prods)):
+                t = P.r64("t")
+                if idx == 0 and first_addend is not None:
+                    x64 = P.r64("x")
+                    P.emit("pack", x64, first_addend, 0)
+                    P.emit("mad.wide.u32", t, u, v, x64)
+                else:
+                    P.emit("mul.wide.u32", t, u, v)
+                if c in L:
+                    P.emit("addc.cc.u64" if carrying else "add.cc.u64", L[c], L[c], t)
+                    carrying = True
+                else:
+                    if carrying:
+                        L[c] = P.r64("L")
+                        P.emit("addc.cc.u64", L[c], t, 0)
+                    else:
+                        L[c] = t
+            if carry_lane is None:
+                if carrying:
+                    P.emit("assert_nc", None)
+            elif carrying:
+                if carry_lane in L:
+                    P.emit("addc.u64", L[carry_lane], L[carry_lane], 0)
+                else:
+                    L[carry_lane] = P.r64("L")
+                    P.emit("addc.u64", L[carry_lane], 0, 0)
+
+        for i in range(N):
+            ev = list(range(0, N, 2))
+            od = list(range(1, N, 2))
+            chain([i + j for j in ev], [(a[j], b[i]) for j in ev], i + N, first_addend=x)
+            chain([i + j for j in od], [(a[j], b[i]) for j in od], None)
+            lo, hi = P.r32("lo"), P.r32("hi")
+            P.emit("unpack", (lo, hi), L[i])
+            m = P.r32("m")
+            P.emit("mul.lo.u32", m, lo, self.m32)
+            chain([i + j for j in ev], [(m, self.pl[j]) for j in ev], i + N)
+            chain([i + j for j in od], [(m, self.pl[j]) for j in od], None)
+            P.emit("assert_lo0", None, L[i])
+            lo2, hi2 = P.r32("z"), P.r32("x")
+            P.emit("unpack", (lo2, hi2), L[i])
+            x = hi2
+            del L[i]
+        # merge: even family lanes L[N], L[N+2], ... ; odd family: x at col N, L[N+1].. L[2N-1]
+        odd32 = {N: x}
+        for c in range(N + 1, 2 * N, 2):
+            if c in L:
+                lo, hi = P.r32("ol"), P.r32("oh")
+                P.emit("unpack", (lo, hi), L[c])
+                odd32[c] = lo
+                if c + 1 < 2 * N:
+                    odd32[c + 1] = hi
+        res = []
+        for k in range(N2):
+            c = N + 2 * k
+            o64 = P.r64("o")
+            P.emit("pack", o64, odd32.get(c, 0), odd32.get(c + 1, 0))
+            lane = L.get(c)
+            if lane is None:
+                lane = P.r64("L")
+                P.emit("mov.u64", lane, 0)
+            P.emit("add.cc.u64" if k == 0 else "addc.cc.u64", lane, lane, o64)
+            res.append(lane)
+        P.emit("assert_nc", None)
+        self._final_sub(P, res, outs)
+        return P, outs, ain + bin_
+
+    def gen_add(self):
+        N2 = self.N2
+        P = Prog()
+        outs = [f"r{k}" for k in range(N2)]
+        ain = [f"a{k}" for k in range(N2)]
+        bin_ = [f"b{k}" for k in range(N2)]
+        s = [P.r64("s") for _ in range(N2)]
+        for k in range(N2):
+            P.emit("add.cc.u64" if k == 0 else "addc.cc.u64", s[k], ain[k], bin_[k])
+        P.emit("assert_nc", None)
+        self._final_sub(P, s, outs)
+        return P, outs, ain + bin_
+
+    def gen_sub(self):
+        N2 = self.N2
+        P = Prog()
+        outs = [f"r{k}" for k in range(N2)]
+        ain = [f"a{k}" for k in range(N2)]
+        bin_ = [f"b{k}" for k in range(N2)]
+        d = [P.r64("d") for _ in range(N2)]
+        for k in range(N2):
+            P.emit("sub.cc.u64" if k == 0 else "subc.cc.u64", d[k], ain[k], bin_[k])
+        bw = P.r32("bw")
+        P.emit("subc.u32", bw, 0, 0)
+        pr = P.pred()
+        P.emit("setp.ne.u32", pr, bw, 0)
+        # add back p when a < b
+        for k in range(N2):
+            pm = P.r64("pm")
+            P.emit("selp.b64", pm, self.p64[k], 0, pr)
+            P.emit("add.cc.u64" if k == 0 else "addc.cc.u64", outs[k], d[k], pm)
+        return P, outs, ain + bin_
+
+    # ---------- emit C++ ----------
+    def cpp_fn(self, fname, P, outs, ins, out_early_clobber=False):
+        omap = {}
+        k = 0
+        for o in outs:
+            omap[o] = f"%{k}"
+            k += 1
+        for i_ in ins:
+            omap[i_] = f"%{k}"
+            k += 1
+        lines = P.ptx(omap)
+        body = "\n".join('        "' + ln + '\\n\\t"' for ln in ["{"] + lines + ["}"])
+        n2 = self.N2
+        cons = "=&l" if out_early_clobber else "=l"
+        outc = ", ".join(f'"{cons}"(r.v[{i}])' for i in range(n2))
+        nin = len(ins) // n2
+        names = ["a", "b"][:nin]
+        inc = ", ".join(f'"l"({nm}.v[{i}])' for nm in names for i in range(n2))
+        args = ", ".join(f"const {self.name}_t& {nm}" for nm in names)
+        return (f"__device__ __forceinline__ void {self.name}_{fname}({self.name}_t& r, {args}) {{\n"
+                f"    asm(\n{body}\n        : {outc}\n        : {inc});\n}}\n")
+
+
+def field_list():
+    from oracle.params import BLS12_381, BN254
+    return [
+        ("bls12_381_fq", BLS12_381.p),
+        ("bls12_381_fr", BLS12_381.r),
+        ("bn254_fq", BN254.p),
+        ("bn254_fr", BN254.r),
+    ]
+
+
+def extra_constants():
+    """Fr-only constants (Montgomery form): 2-adic root of unity and F::GENERATOR
+    (ark-ff FftField::TWO_ADIC_ROOT_OF_UNITY / GENERATOR)."""
+    from oracle.params import BLS12_381, BN254
+    out = {}
+    for c in (BLS12_381, BN254):
+        R = 1 << 256
+        out[c.name + "_fr"] = [
+            ("ROOT", c.two_adic_root * R % c.r, "TWO_ADIC_ROOT_OF_UNITY * R mod r"),
+            ("GEN", c.fr_generator * R % c.r, "F::GENERATOR * R mod r"),
+        ]
+    return out
+
+
+def c_array64(x, n2):
+    return "{" + ", ".join(f"0x{v:016x}ull" for v in lanes64(x, n2)) + "}"
+
+
+def emit_header(path):
+    out = []
+    out.append("// GENERATED by tools/gen_field.py -- do not edit.  Regenerate: python tools/gen_field.py\n"
+               "// Montgomery arithmetic for sm_100a as fully unrolled PTX; see the generator for the\n"
+               "// algorithm and tests/test_field_gen.py for the instruction-level verification.\n"
+               "#pragma once\n#include <cstdint>\n\nnamespace hk {\n")
+    for name, p in field_list():
+        fg = FieldGen(name, p)
+        n2 = fg.N2
+        R = fg.R
+        out.append(f"// ---------------- {name}: {p.bit_length()} bits, {fg.N} x 32-bit limbs ----------------\n")
+        out.append(f"struct alignas(16) {name}_t {{ uint64_t v[{n2}]; }};\n")
+        out.append(f"struct {name}_params {{\n"
+                   f"    static constexpr int N64 = {n2};\n"
+                   f"    static constexpr int BITS = {p.bit_length()};\n"
+                   f"    static constexpr uint32_t M32 = 0x{fg.m32:08x}u;\n"
+                   f"}};\n")
+        out.append(f"__device__ __constant__ const uint64_t {name}_MOD[{n2}] = {c_array64(p, n2)};\n")
+        out.append(f"__device__ __constant__ const uint64_t {name}_ONE[{n2}] = {c_array64(R % p, n2)};   // R mod p\n")
+        out.append(f"__device__ __constant__ const uint64_t {name}_R2[{n2}] = {c_array64(R * R % p, n2)};    // R^2 mod p\n")
+        for cname, val, doc in extra_constants().get(name, []):
+            out.append(f"__device__ __constant__ const uint64_t {name}_{cname}[{n2}] = {c_array64(val, n2)};   // {doc}\n")
+        for fname, gen in (("mul", fg.gen_mul), ("add", fg.gen_add), ("sub", fg.gen_sub)):
+            P, outs, ins = gen()
+            out.append(fg.cpp_fn(fname, P, outs, ins))
+        out.append("\n")
+    out.append("}  // namespace hk\n")
+    with open(path, "w") as f:
+        f.write("".join(out))
+
+
+def selftest(iters=200, seed=1):
+    rng = random.Random(seed)
+    for name, p in field_list():
+        fg = FieldGen(name, p)
+        n2 = fg.N2
+        R = fg.R
+        Rinv = pow(R, -1, p)
+        progs = {k: g() for k, g in (("mul", fg.gen_mul), ("add", fg.gen_add), ("sub", fg.gen_sub))}
+        edge = [0, 1, 2, p - 1, p - 2, R % p, (R * R) % p, (p - 1) // 2, (1 << (p.bit_length() - 1)),
+                (1 << (p.bit_length() - 1)) - 1, p - (1 << 64), (1 << 64) - 1, (1 << 32) - 1]
+        edge = [e % p for e in edge]
+        cases = [(x, y) for x in edge for y in edge]
+        cases += [(rng.randrange(p), rng.randrange(p)) for _ in range(iters)]
+        for x, y in cases:
+            env = {}
+            for k in range(n2):
+                env[f"a{k}"] = lanes64(x, n2)[k]
+                env[f"b{k}"] = lanes64(y, n2)[k]
+            for op, ref in (("mul", x * y * Rinv % p), ("add", (x + y) % p), ("sub", (x - y) % p)):
+                P, outs, ins = progs[op]
+                Rr = P.run(env)
+                got = sum(Rr[o] << (64 * k) for k, o in enumerate(outs))
+                assert got == ref, (name, op, hex(x), hex(y), hex(got), hex(ref))
+        nmul = sum(1 for op, _, _ in progs["mul"][0].ins if op in ("mul.wide.u32", "mad.wide.u32"))
+        print(f"{name}: ok  ({len(cases)} cases; mul = {nmul} wide multiplies, "
+              f"{len(progs['mul'][0].ins)} PTX instructions)")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..",
+                                                  "hekaton_system_b200", "csrc", "field_gen.cuh"))
+    ap.add_argument("--selftest", action="store_true")
+    args = ap.parse_args()
+    if args.selftest:
+        selftest()
+    else:
+        emit_header(args.out)
+        print("wrote", os.path.abspath(args.out))
