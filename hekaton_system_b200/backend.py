@@ -124,7 +124,15 @@ class Context:
         self.lib = load_library()
         self.curve = get_curve(curve)
         h = C.c_void_p()
-        rc = self.lib.hk_ctx_create(int(device), self.curve.cid, C.c_void_p(stream) if stream else None, C.byref(h))
+        # stream: None -> the library creates a private stream; 0 -> the legacy default stream
+        # (cudaStreamLegacy = 0x1, which is what torch's default stream is); else a cudaStream_t
+        if stream is None:
+            sp = None
+        elif int(stream) == 0:
+            sp = C.c_void_p(1)
+        else:
+            sp = C.c_void_p(int(stream))
+        rc = self.lib.hk_ctx_create(int(device), self.curve.cid, sp, C.byref(h))
         if rc != 0:
             raise HkError(rc, "hk_ctx_create failed (an sm_100 GPU is required; there is no CPU fallback)")
         self.h = h

@@ -58,7 +58,7 @@ def test_ntt_large_properties(ctx, log_n):
     cv = ctx.curve
     n = 1 << log_n
     rng = np.random.default_rng(log_n)
-    a = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)   # < r as raw Montgomery residues
+    a = rng.integers(0, 1 << 60, size=(n, 4), dtype=np.uint64)   # < r (both curves) as raw Montgomery residues
     orig = a.copy()
     for coset in (False, True):
         ctx.ntt(a, log_n, coset=coset)
