@@ -1,6 +1,8 @@
 /* Montgomery prime field with NL 64-bit limbs -- template body, include with:
- *   #define FP      name prefix (e.g. bls_fq)
- *   #define NL      limb count (4 or 6)
+ *   #define FP        name prefix (e.g. bls_fq)
+ *   #define NL        limb count (4 or 6)
+ *   #define MOD_INIT  {limbs...}  modulus, little-endian (compile-time constant)
+ *   #define INV_CONST -p^-1 mod 2^64
  * Restates ark-ff 0.4 `Fp<MontBackend<_,N>,N>` (third-party, un-vendored; B.4 of SURVEY.md):
  * little-endian u64 limbs, Montgomery form R = 2^(64 NL), CIOS multiplication.
  * ORACLE / CPU BASELINE ONLY -- test infrastructure, never linked into the product. */
@@ -10,8 +12,9 @@
 
 typedef struct { uint64_t v[NL]; } F(t);
 
-static F(t) F(MOD), F(ONE), F(R2);
-static uint64_t F(INV);     /* -p^-1 mod 2^64 */
+static const F(t) F(MOD) = {MOD_INIT};
+static F(t) F(ONE), F(R2);
+static const uint64_t F(INV) = INV_CONST;     /* -p^-1 mod 2^64 */
 
 static inline int F(is_zero)(const F(t) * a) {
     uint64_t o = 0;
@@ -71,12 +74,13 @@ static inline void F(neg)(F(t) * r, const F(t) * a) {
     F(t) z; memset(&z, 0, sizeof z);
     F(sub)(r, &z, a);
 }
-/* CIOS Montgomery product */
-static inline void F(mul)(F(t) * r, const F(t) * a, const F(t) * b) {
-    uint64_t t[NL + 2];
-    memset(t, 0, sizeof t);
+/* CIOS Montgomery product (fully unrolled; branch-free final subtraction) */
+static inline __attribute__((always_inline)) void F(mul)(F(t) * r, const F(t) * a, const F(t) * b) {
+    uint64_t t[NL + 2] = {0};
+#pragma GCC unroll 8
     for (int i = 0; i < NL; i++) {
         unsigned __int128 c = 0;
+#pragma GCC unroll 8
         for (int j = 0; j < NL; j++) {
             c += (unsigned __int128)a->v[j] * b->v[i] + t[j];
             t[j] = (uint64_t)c;
@@ -88,6 +92,7 @@ static inline void F(mul)(F(t) * r, const F(t) * a, const F(t) * b) {
         uint64_t m = t[0] * F(INV);
         c = (unsigned __int128)m * F(MOD).v[0] + t[0];
         c >>= 64;
+#pragma GCC unroll 8
         for (int j = 1; j < NL; j++) {
             c += (unsigned __int128)m * F(MOD).v[j] + t[j];
             t[j - 1] = (uint64_t)c;
@@ -97,10 +102,17 @@ static inline void F(mul)(F(t) * r, const F(t) * a, const F(t) * b) {
         t[NL - 1] = (uint64_t)c;
         t[NL] = t[NL + 1] + (uint64_t)(c >> 64);
     }
-    F(t) o;
-    for (int i = 0; i < NL; i++) o.v[i] = t[i];
-    if (t[NL] || F(geq_mod)(&o)) F(sub_mod_raw)(&o);
-    *r = o;
+    uint64_t s[NL];
+    unsigned __int128 bw = 0;
+#pragma GCC unroll 8
+    for (int i = 0; i < NL; i++) {
+        unsigned __int128 d = (unsigned __int128)t[i] - F(MOD).v[i] - (uint64_t)bw;
+        s[i] = (uint64_t)d;
+        bw = (d >> 64) & 1;
+    }
+    int ge = (t[NL] != 0) | (bw == 0);
+#pragma GCC unroll 8
+    for (int i = 0; i < NL; i++) r->v[i] = ge ? s[i] : t[i];
 }
 static inline void F(sqr)(F(t) * r, const F(t) * a) { F(mul)(r, a, a); }
 static inline void F(from_mont)(F(t) * r, const F(t) * a) {
@@ -123,11 +135,11 @@ static void F(inv)(F(t) * r, const F(t) * a) {
     *r = acc;
 }
 static void F(init)(const uint64_t* mod) {
-    for (int i = 0; i < NL; i++) F(MOD).v[i] = mod[i];
-    /* inv = -p^-1 mod 2^64 by Newton iteration */
+    for (int i = 0; i < NL; i++) if (F(MOD).v[i] != mod[i]) abort();
+    /* check inv = -p^-1 mod 2^64 by Newton iteration */
     uint64_t p0 = mod[0], x = 1;
     for (int i = 0; i < 6; i++) x *= 2 - p0 * x;
-    F(INV) = (uint64_t)(0 - x);
+    if (F(INV) != (uint64_t)(0 - x)) abort();
     /* R mod p by doubling 1, 64*NL times; R2 by another 64*NL doublings */
     F(t) one; memset(&one, 0, sizeof one); one.v[0] = 1;
     F(t) x1 = one;

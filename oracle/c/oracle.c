@@ -45,24 +45,40 @@ static void ark_make_digits(const uint64_t a[4], int w, int num_bits, int32_t* d
 /* ---- field / group instantiations -------------------------------------------------------------- */
 #define FP bls_fq
 #define NL 6
+#define MOD_INIT {0xb9feffffffffaaabull, 0x1eabfffeb153ffffull, 0x6730d2a0f6b0f624ull, 0x64774b84f38512bfull, 0x4b1ba7b6434bacd7ull, 0x1a0111ea397fe69aull}
+#define INV_CONST 0x89f3fffcfffcfffdull
 #include "field_tmpl.h"
 #undef FP
 #undef NL
+#undef MOD_INIT
+#undef INV_CONST
 #define FP bls_fr
 #define NL 4
+#define MOD_INIT {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull}
+#define INV_CONST 0xfffffffeffffffffull
 #include "field_tmpl.h"
 #undef FP
 #undef NL
+#undef MOD_INIT
+#undef INV_CONST
 #define FP bn_fq
 #define NL 4
+#define MOD_INIT {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull}
+#define INV_CONST 0x87d20782e4866389ull
 #include "field_tmpl.h"
 #undef FP
 #undef NL
+#undef MOD_INIT
+#undef INV_CONST
 #define FP bn_fr
 #define NL 4
+#define MOD_INIT {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull}
+#define INV_CONST 0xc2e1f593efffffffull
 #include "field_tmpl.h"
 #undef FP
 #undef NL
+#undef MOD_INIT
+#undef INV_CONST
 #define FP2 bls_fq2
 #define FPB bls_fq
 #include "fp2_tmpl.h"
