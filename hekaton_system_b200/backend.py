@@ -86,6 +86,9 @@ def load_library(path=None):
         "hk_field_op": [vp, u32, u32, u64p, u64p, u64p, sz],
         "hk_bench_field_mul": [vp, u32, u32, u32, C.POINTER(C.c_float)],
         "hk_bench_imad_wide": [vp, u32, C.POINTER(C.c_double)],
+        "hk_profile_enable": [vp, i32],
+        "hk_profile_reset": [vp],
+        "hk_profile_read": [vp, u32, C.POINTER(C.c_double), C.POINTER(u64), C.POINTER(u64)],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -336,6 +339,18 @@ class Context:
         self._ck(self.lib.hk_field_op(self.h, field, op, a.ctypes.data, b.ctypes.data if b is not None else None,
                                       out.ctypes.data, n))
         return out
+
+    def profile(self, on=True):
+        self._ck(self.lib.hk_profile_enable(self.h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._ck(self.lib.hk_profile_reset(self.h))
+
+    def profile_read(self, kernel_id):
+        """-> (total_ms, launches, units) for PROF_MSM_ACCUM_G1 (0), _G2 (1), PROF_NTT_PASS (2)."""
+        ms, n, u = C.c_double(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.hk_profile_read(self.h, kernel_id, C.byref(ms), C.byref(n), C.byref(u)))
+        return ms.value, n.value, u.value
 
     def bench_field_mul(self, field, threads, iters):
         ms = C.c_float()

@@ -100,14 +100,19 @@ class ProvingKey:
     @classmethod
     def from_handles(cls, ctx, staged, h_a, h_b1, h_h, h_b2, h_ck, h_d, alpha_g, beta_g, beta_h, last_delta_h):
         cv = ctx.curve
+        return cls.from_handles_raw(ctx, staged, h_a, h_b1, h_h, h_b2, h_ck, h_d,
+                                    codec.g1_affine_to_limbs([alpha_g], cv)[0][0], codec.g1_affine_to_limbs([beta_g], cv)[0][0],
+                                    codec.g2_affine_to_limbs([beta_h], cv)[0][0],
+                                    codec.g2_affine_to_limbs([last_delta_h], cv)[0][0])
+
+    @classmethod
+    def from_handles_raw(cls, ctx, staged, h_a, h_b1, h_h, h_b2, h_ck, h_d, alpha_g, beta_g, beta_h, last_delta_h):
+        """Same, with the four loose vk points already as Montgomery limb arrays."""
         n = staged.num_constraints
         nw = len(staged.witness)
         r1 = ctx.r1cs_upload(n, staged.l, nw, staged.csr())
         starts = [s for s, _ in staged.stage_ranges] + [staged.stage_ranges[-1][1]]
-        pk = ctx.pk_create(h_a, h_b1, h_h, h_b2, h_ck, h_d,
-                           codec.g1_affine_to_limbs([alpha_g], cv)[0], codec.g1_affine_to_limbs([beta_g], cv)[0],
-                           codec.g2_affine_to_limbs([beta_h], cv)[0], codec.g2_affine_to_limbs([last_delta_h], cv)[0],
-                           r1, starts)
+        pk = ctx.pk_create(h_a, h_b1, h_h, h_b2, h_ck, h_d, alpha_g, beta_g, beta_h, last_delta_h, r1, starts)
         log_n = max(1, (n + staged.l - 1).bit_length())
         return cls(ctx, pk, len(h_ck), staged.l, nw, log_n)
 

@@ -33,6 +33,16 @@ const void* to_device(hk_ctx* ctx, DevBuf& buf, const void* p, size_t bytes, uin
 
 uint64_t new_handle(hk_ctx* ctx) { return ctx->next_handle++; }
 
+void prof_clear(hk_ctx* ctx) {
+    for (auto& r : ctx->prof) {
+        if (r.e0) cudaEventDestroy(r.e0);
+        if (r.e1) cudaEventDestroy(r.e1);
+    }
+    ctx->prof.clear();
+    ctx->prof_pinned_used = 0;
+}
+
+
 BaseSet& find_bases(hk_ctx* ctx, uint64_t h, int group) {
     auto it = ctx->bases.find(h);
     HK_REQUIRE(it != ctx->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
@@ -277,6 +287,8 @@ HK_EXPORT int32_t hk_ctx_destroy(hk_ctx* ctx) {
     if (!ctx) return HK_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    prof_clear(ctx);
+    if (ctx->prof_pinned) cudaFreeHost(ctx->prof_pinned);
     ctx->pks.clear();
     ctx->r1cs.clear();
     ctx->domains.clear();
@@ -595,6 +607,39 @@ HK_EXPORT int32_t hk_field_op(hk_ctx* ctx, uint32_t field, uint32_t op, const ui
         } else {
             throw HkError{HK_ERR_INVALID, "bad field id"};
         }
+    });
+}
+
+HK_EXPORT int32_t hk_profile_enable(hk_ctx* ctx, int32_t on) {
+    return guarded(ctx, [&] {
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->prof_on = on != 0;
+    });
+}
+HK_EXPORT int32_t hk_profile_reset(hk_ctx* ctx) {
+    return guarded(ctx, [&] {
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        prof_clear(ctx);
+    });
+}
+HK_EXPORT int32_t hk_profile_read(hk_ctx* ctx, uint32_t kernel_id, double* total_ms, uint64_t* launches,
+                                  uint64_t* units) {
+    return guarded(ctx, [&] {
+        HK_REQUIRE(kernel_id < HK_PROF_COUNT && total_ms && launches && units, HK_ERR_INVALID, "bad argument");
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        double ms = 0;
+        uint64_t n = 0, u = 0;
+        for (auto& r : ctx->prof) {
+            if (r.id != (int)kernel_id) continue;
+            float t = 0;
+            HK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+            ms += t;
+            n++;
+            u += r.pinned_units ? (uint64_t)*r.pinned_units : r.static_units;
+        }
+        *total_ms = ms;
+        *launches = n;
+        *units = u;
     });
 }
 

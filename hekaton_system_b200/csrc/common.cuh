@@ -120,6 +120,13 @@ struct BaseSet {
     }
 };
 
+struct ProfRec {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int id = 0;
+    uint64_t static_units = 0;
+    uint32_t* pinned_units = nullptr;   // filled by an async D2H copy of a device counter
+};
+
 struct NttDomain;   // ntt.cu
 struct R1csDev;     // qap.cu
 struct PkDev;       // prove.cu
@@ -146,6 +153,13 @@ struct hk_ctx {
     hk::DevBuf ws_ntt_tmp, ws_qap[4], ws_io[4], ws_z, ws_misc;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
+
+    // roofline profiling (hk_profile_*)
+    bool prof_on = false;
+    std::vector<hk::ProfRec> prof;
+    uint32_t* prof_pinned = nullptr;
+    size_t prof_pinned_used = 0;
+    static constexpr size_t PROF_SLOTS = 1 << 16;
 
     void* pinned_buf(size_t bytes) {
         if (bytes > pinned_cap) {
@@ -190,6 +204,31 @@ inline int32_t guarded(hk_ctx* ctx, Fn&& fn) {
         (ctx)->launches++;         \
         HK_CUDA(cudaGetLastError()); \
     } while (0)
+
+// Bracket one kernel launch with events when profiling is on.
+inline int prof_begin(hk_ctx* ctx, int id) {
+    if (!ctx->prof_on) return -1;
+    ProfRec r;
+    r.id = id;
+    HK_CUDA(cudaEventCreate(&r.e0));
+    HK_CUDA(cudaEventCreate(&r.e1));
+    HK_CUDA(cudaEventRecord(r.e0, ctx->stream));
+    ctx->prof.push_back(r);
+    return (int)ctx->prof.size() - 1;
+}
+inline void prof_end(hk_ctx* ctx, int idx, uint64_t static_units, const uint32_t* d_units) {
+    if (idx < 0) return;
+    ProfRec& r = ctx->prof[idx];
+    HK_CUDA(cudaEventRecord(r.e1, ctx->stream));
+    r.static_units = static_units;
+    if (d_units) {
+        if (!ctx->prof_pinned) HK_CUDA(cudaMallocHost((void**)&ctx->prof_pinned, hk_ctx::PROF_SLOTS * sizeof(uint32_t)));
+        if (ctx->prof_pinned_used < hk_ctx::PROF_SLOTS) {
+            r.pinned_units = ctx->prof_pinned + ctx->prof_pinned_used++;
+            HK_CUDA(cudaMemcpyAsync(r.pinned_units, d_units, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+}
 
 // ---- per-module entry points (implemented in the respective .cu files) -----------------
 // msm: bases/scalars are device pointers; out_xyzz receives K XYZZ points (device).

@@ -410,9 +410,11 @@ void msm_run(hk_ctx* ctx, const void* d_bases_v, size_t n, const Scalar256* d_sc
         exclusive_scan_u32(ctx, hist, nkeys, d_count);
         k_msm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(d_sc, n, pl.c, pl.W, pl.B, hist, items, keys);
         HK_LAUNCH_CHECK(ctx);
+        int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2);
         k_msm_accum<F, S0><<<ceil_div(nthr0, 128), 128, 0, st>>>(d_bases, items, keys, d_count, buckets, partial,
                                                                partial_keys, nthr0);
         HK_LAUNCH_CHECK(ctx);
+        prof_end(ctx, pi, 0, d_count);
         size_t off = 0;
         for (size_t l = 0; l < lvl_in.size(); l++) {
             uint32_t n_in = lvl_in[l];

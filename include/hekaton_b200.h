@@ -188,6 +188,15 @@ int32_t hk_field_op(hk_ctx* ctx, uint32_t field, uint32_t op, const uint64_t* a,
 /* Dependent-chain multiply throughput probe: `iters` Montgomery multiplies per thread on
  * `threads` threads; returns elapsed milliseconds (CUDA events on the context stream). */
 int32_t hk_bench_field_mul(hk_ctx* ctx, uint32_t field, uint32_t threads, uint32_t iters, float* ms);
+/* Per-kernel timing for the roofline report.  While enabled, the dominant kernels are bracketed
+ * by CUDA events on the context stream and their work counts are recorded:
+ *   HK_PROF_MSM_ACCUM_G1 / _G2  units = bucket-accumulation point additions
+ *   HK_PROF_NTT_PASS            units = field elements read+written by a pass
+ * hk_profile_read synchronises the stream and returns totals since the last reset. */
+enum { HK_PROF_MSM_ACCUM_G1 = 0, HK_PROF_MSM_ACCUM_G2 = 1, HK_PROF_NTT_PASS = 2, HK_PROF_COUNT = 3 };
+int32_t hk_profile_enable(hk_ctx* ctx, int32_t on);
+int32_t hk_profile_reset(hk_ctx* ctx);
+int32_t hk_profile_read(hk_ctx* ctx, uint32_t kernel_id, double* total_ms, uint64_t* launches, uint64_t* units);
 /* Raw IMAD.WIDE.U32 issue-rate probe (the MSM roofline denominator): returns wide
  * multiply-accumulates per second. */
 int32_t hk_bench_imad_wide(hk_ctx* ctx, uint32_t iters, double* macs_per_s);
