@@ -57,6 +57,8 @@ def load_library(path=None):
     sigs = {
         "hk_ctx_create": [C.c_int, u32, vp, C.POINTER(vp)],
         "hk_ctx_destroy": [vp],
+        "hk_ctx_fork": [vp, vp, C.POINTER(vp)],
+        "hk_bases_precompute": [vp, u64],
         "hk_ctx_sync": [vp],
         "hk_curve_info": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)],
         "hk_bases_upload_g1": [vp, vp, u8p, sz, u32, C.POINTER(u64)],
@@ -123,10 +125,11 @@ class Context:
     """One GPU, one stream.  `stream` = a cudaStream_t value (e.g.
     torch.cuda.current_stream().cuda_stream) or None for a private stream."""
 
-    def __init__(self, curve="bls12_381", device=0, stream=None):
+    def __init__(self, curve="bls12_381", device=0, stream=None, _parent=None):
         self.lib = load_library()
         self.curve = get_curve(curve)
         h = C.c_void_p()
+        self._parent = _parent          # keeps the parent alive as long as a fork exists
         # stream: None -> the library creates a private stream; 0 -> the legacy default stream
         # (cudaStreamLegacy = 0x1, which is what torch's default stream is); else a cudaStream_t
         if stream is None:
@@ -135,12 +138,20 @@ class Context:
             sp = C.c_void_p(1)
         else:
             sp = C.c_void_p(int(stream))
-        rc = self.lib.hk_ctx_create(int(device), self.curve.cid, sp, C.byref(h))
+        if _parent is not None:
+            rc = self.lib.hk_ctx_fork(_parent.h, sp, C.byref(h))
+        else:
+            rc = self.lib.hk_ctx_create(int(device), self.curve.cid, sp, C.byref(h))
         if rc != 0:
             raise HkError(rc, "hk_ctx_create failed (an sm_100 GPU is required; there is no CPU fallback)")
         self.h = h
         self.device = device
         self.L = self.curve.fq_limbs
+
+    def fork(self, stream=None):
+        """A context sharing this one's uploaded resources (same handles) with its own stream and
+        scratch memory -- one per concurrently running proof / host thread."""
+        return Context(self.curve, self.device, stream, _parent=self)
 
     def close(self):
         if getattr(self, "h", None):
@@ -206,6 +217,9 @@ class Context:
         out = np.zeros((n, (2 if group == 1 else 4) * self.L), dtype=np.uint64)
         self._ck(self.lib.hk_bases_download(self.h, handle, offset, n, out.ctypes.data))
         return out
+
+    def bases_precompute(self, handle):
+        self._ck(self.lib.hk_bases_precompute(self.h, handle))
 
     def bases_free(self, handle):
         self._ck(self.lib.hk_bases_free(self.h, handle))

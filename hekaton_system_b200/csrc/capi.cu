@@ -31,7 +31,10 @@ const void* to_device(hk_ctx* ctx, DevBuf& buf, const void* p, size_t bytes, uin
     return d;
 }
 
-uint64_t new_handle(hk_ctx* ctx) { return ctx->next_handle++; }
+uint64_t new_handle(hk_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(ctx->sh->mu);
+    return ctx->sh->next_handle++;
+}
 
 void prof_clear(hk_ctx* ctx) {
     for (auto& r : ctx->prof) {
@@ -43,18 +46,41 @@ void prof_clear(hk_ctx* ctx) {
 }
 
 
-BaseSet& find_bases(hk_ctx* ctx, uint64_t h, int group) {
-    auto it = ctx->bases.find(h);
-    HK_REQUIRE(it != ctx->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
-    HK_REQUIRE(it->second->group == group, HK_ERR_INVALID, "base set belongs to the other group");
-    return *it->second;
+std::shared_ptr<BaseSet> find_bases_any(hk_ctx* ctx, uint64_t h) {
+    std::lock_guard<std::mutex> lk(ctx->sh->mu);
+    auto it = ctx->sh->bases.find(h);
+    HK_REQUIRE(it != ctx->sh->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
+    return it->second;
+}
+std::shared_ptr<BaseSet> find_bases(hk_ctx* ctx, uint64_t h, int group) {
+    auto bs = find_bases_any(ctx, h);
+    HK_REQUIRE(bs->group == group, HK_ERR_INVALID, "base set belongs to the other group");
+    return bs;
+}
+void register_bases(hk_ctx* ctx, std::shared_ptr<BaseSet> bs, uint64_t* handle) {
+    uint64_t h = new_handle(ctx);
+    std::lock_guard<std::mutex> lk(ctx->sh->mu);
+    ctx->sh->bases[h] = std::move(bs);
+    *handle = h;
+}
+std::shared_ptr<PkDev> find_pk(hk_ctx* ctx, uint64_t h) {
+    std::lock_guard<std::mutex> lk(ctx->sh->mu);
+    auto it = ctx->sh->pks.find(h);
+    HK_REQUIRE(it != ctx->sh->pks.end(), HK_ERR_HANDLE, "unknown pk handle");
+    return it->second;
+}
+std::shared_ptr<R1csDev> find_r1cs(hk_ctx* ctx, uint64_t h) {
+    std::lock_guard<std::mutex> lk(ctx->sh->mu);
+    auto it = ctx->sh->r1cs.find(h);
+    HK_REQUIRE(it != ctx->sh->r1cs.end(), HK_ERR_HANDLE, "unknown r1cs handle");
+    return it->second;
 }
 
 void bases_upload(hk_ctx* ctx, int group, const void* pts, const uint8_t* inf, size_t n, uint32_t memspace,
                   uint64_t* handle) {
     HK_REQUIRE(handle, HK_ERR_INVALID, "handle is NULL");
     HK_REQUIRE(pts || n == 0, HK_ERR_INVALID, "points pointer is NULL");
-    auto bs = std::make_unique<BaseSet>();
+    auto bs = std::make_shared<BaseSet>();
     bs->group = group;
     bs->n = n;
     bs->point_bytes = point_bytes(ctx, group);
@@ -69,15 +95,13 @@ void bases_upload(hk_ctx* ctx, int group, const void* pts, const uint8_t* inf, s
         by_curve(ctx, [&] { apply_infinity<Bls12381>(ctx, *bs, d_inf); }, [&] { apply_infinity<Bn254>(ctx, *bs, d_inf); });
     }
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
-    uint64_t h = new_handle(ctx);
-    ctx->bases[h] = std::move(bs);
-    *handle = h;
+    register_bases(ctx, bs, handle);
 }
 
 void bases_from_scalars(hk_ctx* ctx, int group, const void* gen, const uint64_t* scalars, size_t n, uint32_t repr,
                         uint32_t memspace, uint64_t* handle) {
     HK_REQUIRE(handle && gen, HK_ERR_INVALID, "NULL argument");
-    auto bs = std::make_unique<BaseSet>();
+    auto bs = std::make_shared<BaseSet>();
     bs->group = group;
     bs->n = n;
     bs->point_bytes = point_bytes(ctx, group);
@@ -93,9 +117,7 @@ void bases_from_scalars(hk_ctx* ctx, int group, const void* gen, const uint64_t*
         by_curve(ctx, [&] { fixed_base_mul<Bls12381, 2>(ctx, d_gen, d_sc, n, mont, bs->d); },
                  [&] { fixed_base_mul<Bn254, 2>(ctx, d_gen, d_sc, n, mont, bs->d); });
     HK_CUDA(cudaStreamSynchronize(ctx->stream));
-    uint64_t h = new_handle(ctx);
-    ctx->bases[h] = std::move(bs);
-    *handle = h;
+    register_bases(ctx, bs, handle);
 }
 
 void msm_entry(hk_ctx* ctx, int group, uint64_t bases, size_t base_offset, const uint64_t* scalars, size_t n, size_t K,
@@ -103,7 +125,8 @@ void msm_entry(hk_ctx* ctx, int group, uint64_t bases, size_t base_offset, const
     HK_REQUIRE(out, HK_ERR_INVALID, "out is NULL");
     HK_REQUIRE(scalars || n == 0, HK_ERR_INVALID, "scalars is NULL");
     HK_REQUIRE(repr == HK_SCALAR_BIGINT || repr == HK_SCALAR_MONT, HK_ERR_INVALID, "bad scalar_repr");
-    BaseSet& bs = find_bases(ctx, bases, group);
+    std::shared_ptr<BaseSet> bsp = find_bases(ctx, bases, group);
+    BaseSet& bs = *bsp;
     // msm_unchecked / msm_bigint zip to the shorter of (bases, scalars)
     size_t avail = base_offset < bs.n ? bs.n - base_offset : 0;
     size_t len = n < avail ? n : avail;
@@ -122,14 +145,15 @@ void msm_entry(hk_ctx* ctx, int group, uint64_t bases, size_t base_offset, const
         d_sc = d;
     }
     void* d_out = (memspace == HK_DEVICE) ? out : ctx->ws_out.ensure(jb * K + 64);
-    const char* d_b = (const char*)bs.d + base_offset * bs.point_bytes;
+    const MsmBases bv = msm_view(bs);
+    const size_t off = len ? base_offset : 0;
     bool mont = repr == HK_SCALAR_MONT;
     if (group == 1)
-        by_curve(ctx, [&] { msm_run<Bls12381, 1>(ctx, d_b, len, d_sc, K, mont, d_out); },
-                 [&] { msm_run<Bn254, 1>(ctx, d_b, len, d_sc, K, mont, d_out); });
+        by_curve(ctx, [&] { msm_run<Bls12381, 1>(ctx, bv, off, len, d_sc, K, mont, d_out); },
+                 [&] { msm_run<Bn254, 1>(ctx, bv, off, len, d_sc, K, mont, d_out); });
     else
-        by_curve(ctx, [&] { msm_run<Bls12381, 2>(ctx, d_b, len, d_sc, K, mont, d_out); },
-                 [&] { msm_run<Bn254, 2>(ctx, d_b, len, d_sc, K, mont, d_out); });
+        by_curve(ctx, [&] { msm_run<Bls12381, 2>(ctx, bv, off, len, d_sc, K, mont, d_out); },
+                 [&] { msm_run<Bn254, 2>(ctx, bv, off, len, d_sc, K, mont, d_out); });
     if (memspace != HK_DEVICE) {
         HK_CUDA(cudaMemcpyAsync(out, d_out, jb * K, cudaMemcpyDeviceToHost, ctx->stream));
         HK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -266,6 +290,7 @@ HK_EXPORT int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx
     ctx->device = device;
     ctx->curve = curve;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->sh = std::make_shared<SharedState>();
     if (cudaSetDevice(device) != cudaSuccess) {
         delete ctx;
         return HK_ERR_CUDA;
@@ -289,13 +314,36 @@ HK_EXPORT int32_t hk_ctx_destroy(hk_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     prof_clear(ctx);
     if (ctx->prof_pinned) cudaFreeHost(ctx->prof_pinned);
-    ctx->pks.clear();
-    ctx->r1cs.clear();
-    ctx->domains.clear();
-    ctx->bases.clear();
+    ctx->sh.reset();     // shared resources are freed with the last context that references them
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return HK_OK;
+}
+
+HK_EXPORT int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out) {
+    if (!parent || !out) return HK_ERR_INVALID;
+    *out = nullptr;
+    hk_ctx* ctx = new (std::nothrow) hk_ctx();
+    if (!ctx) return HK_ERR_NOMEM;
+    ctx->device = parent->device;
+    ctx->curve = parent->curve;
+    ctx->sm_count = parent->sm_count;
+    ctx->sh = parent->sh;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) {
+        delete ctx;
+        return HK_ERR_CUDA;
+    }
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return HK_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    *out = ctx;
     return HK_OK;
 }
 
@@ -328,24 +376,32 @@ HK_EXPORT int32_t hk_bases_upload_g2(hk_ctx* ctx, const void* p, const uint8_t* 
 }
 HK_EXPORT int32_t hk_bases_free(hk_ctx* ctx, uint64_t handle) {
     return guarded(ctx, [&] {
-        auto it = ctx->bases.find(handle);
-        HK_REQUIRE(it != ctx->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
         HK_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->bases.erase(it);
+        std::lock_guard<std::mutex> lk(ctx->sh->mu);
+        auto it = ctx->sh->bases.find(handle);
+        HK_REQUIRE(it != ctx->sh->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
+        ctx->sh->bases.erase(it);     // memory is released when the last user (e.g. a pk) drops it
     });
 }
 HK_EXPORT int32_t hk_bases_len(hk_ctx* ctx, uint64_t handle, size_t* n) {
     return guarded(ctx, [&] {
-        auto it = ctx->bases.find(handle);
-        HK_REQUIRE(it != ctx->bases.end() && n, HK_ERR_HANDLE, "unknown base-set handle");
-        *n = it->second->n;
+        HK_REQUIRE(n, HK_ERR_INVALID, "n is NULL");
+        *n = find_bases_any(ctx, handle)->n;
+    });
+}
+HK_EXPORT int32_t hk_bases_precompute(hk_ctx* ctx, uint64_t handle) {
+    return guarded(ctx, [&] {
+        auto bs = find_bases_any(ctx, handle);
+        if (bs->group == 1)
+            by_curve(ctx, [&] { bases_precompute<Bls12381, 1>(ctx, *bs); }, [&] { bases_precompute<Bn254, 1>(ctx, *bs); });
+        else
+            by_curve(ctx, [&] { bases_precompute<Bls12381, 2>(ctx, *bs); }, [&] { bases_precompute<Bn254, 2>(ctx, *bs); });
     });
 }
 HK_EXPORT int32_t hk_bases_download(hk_ctx* ctx, uint64_t handle, size_t offset, size_t n, void* out) {
     return guarded(ctx, [&] {
-        auto it = ctx->bases.find(handle);
-        HK_REQUIRE(it != ctx->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
-        BaseSet& bs = *it->second;
+        auto bsp = find_bases_any(ctx, handle);
+        BaseSet& bs = *bsp;
         HK_REQUIRE(out && offset + n <= bs.n, HK_ERR_INVALID, "range outside the base set");
         if (n == 0) return;
         HK_CUDA(cudaMemcpyAsync(out, (char*)bs.d + offset * bs.point_bytes, n * bs.point_bytes, cudaMemcpyDeviceToHost,
@@ -377,8 +433,8 @@ HK_EXPORT int32_t hk_msm_g1_checked(hk_ctx* ctx, uint64_t bases, size_t off, siz
         HK_REQUIRE(n_bases_expected == n, HK_ERR_LENGTH,
                    "msm: bases and scalars differ in length (min = " +
                        std::to_string(n_bases_expected < n ? n_bases_expected : n) + ")");
-        BaseSet& bs = find_bases(ctx, bases, 1);
-        HK_REQUIRE(off + n <= bs.n, HK_ERR_LENGTH, "msm: base range outside the base set");
+        auto bs = find_bases(ctx, bases, 1);
+        HK_REQUIRE(off + n <= bs->n, HK_ERR_LENGTH, "msm: base range outside the base set");
         msm_entry(ctx, 1, bases, off, sc, n, 1, repr, memspace, out);
     });
 }
@@ -460,24 +516,27 @@ HK_EXPORT int32_t hk_r1cs_upload(hk_ctx* ctx, size_t n, size_t l, size_t nw, con
         uint32_t adic = ctx->curve == HK_CURVE_BLS12_381 ? 32 : 28;
         HK_REQUIRE(m->log_n <= adic, HK_ERR_UNSUPPORTED, "r1cs: domain larger than 2^two_adicity");
         uint64_t h = new_handle(ctx);
-        ctx->r1cs[h] = m;
+        {
+            std::lock_guard<std::mutex> lk(ctx->sh->mu);
+            ctx->sh->r1cs[h] = m;
+        }
         *handle = h;
     });
 }
 HK_EXPORT int32_t hk_r1cs_free(hk_ctx* ctx, uint64_t handle) {
     return guarded(ctx, [&] {
-        auto it = ctx->r1cs.find(handle);
-        HK_REQUIRE(it != ctx->r1cs.end(), HK_ERR_HANDLE, "unknown r1cs handle");
         HK_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->r1cs.erase(it);
+        std::lock_guard<std::mutex> lk(ctx->sh->mu);
+        auto it = ctx->sh->r1cs.find(handle);
+        HK_REQUIRE(it != ctx->sh->r1cs.end(), HK_ERR_HANDLE, "unknown r1cs handle");
+        ctx->sh->r1cs.erase(it);
     });
 }
 HK_EXPORT int32_t hk_qap_witness_map(hk_ctx* ctx, uint64_t r1cs, const uint64_t* z, uint32_t memspace, uint64_t* h) {
     return guarded(ctx, [&] {
-        auto it = ctx->r1cs.find(r1cs);
-        HK_REQUIRE(it != ctx->r1cs.end(), HK_ERR_HANDLE, "unknown r1cs handle");
+        auto msp = find_r1cs(ctx, r1cs);
         HK_REQUIRE(z && h, HK_ERR_INVALID, "NULL argument");
-        R1csDev& m = *it->second;
+        R1csDev& m = *msp;
         const size_t N = size_t(1) << m.log_n;
         const uint64_t* dz = (const uint64_t*)to_device(ctx, ctx->ws_z, z, (m.l + m.nw) * 32, memspace);
         uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N);
@@ -506,26 +565,29 @@ HK_EXPORT int32_t hk_pk_create(hk_ctx* ctx, const hk_pk_desc* desc, uint64_t* pk
         std::shared_ptr<PkDev> pk;
         by_curve(ctx, [&] { pk = pk_create<Bls12381>(ctx, *desc); }, [&] { pk = pk_create<Bn254>(ctx, *desc); });
         uint64_t h = new_handle(ctx);
-        ctx->pks[h] = pk;
+        {
+            std::lock_guard<std::mutex> lk(ctx->sh->mu);
+            ctx->sh->pks[h] = pk;
+        }
         *pk_handle = h;
     });
 }
 HK_EXPORT int32_t hk_pk_free(hk_ctx* ctx, uint64_t pk_handle) {
     return guarded(ctx, [&] {
-        auto it = ctx->pks.find(pk_handle);
-        HK_REQUIRE(it != ctx->pks.end(), HK_ERR_HANDLE, "unknown pk handle");
         HK_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->pks.erase(it);
+        std::lock_guard<std::mutex> lk(ctx->sh->mu);
+        auto it = ctx->sh->pks.find(pk_handle);
+        HK_REQUIRE(it != ctx->sh->pks.end(), HK_ERR_HANDLE, "unknown pk handle");
+        ctx->sh->pks.erase(it);
     });
 }
 
 HK_EXPORT int32_t hk_commit(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, const uint64_t* z, const uint64_t* kappa,
                             uint32_t memspace, void* com_affine, uint8_t* com_inf) {
     return guarded(ctx, [&] {
-        auto it = ctx->pks.find(pk_h);
-        HK_REQUIRE(it != ctx->pks.end(), HK_ERR_HANDLE, "unknown pk handle");
+        auto pksp = find_pk(ctx, pk_h);
         HK_REQUIRE(z && kappa && com_affine, HK_ERR_INVALID, "NULL argument");
-        PkDev& pk = *it->second;
+        PkDev& pk = *pksp;
         HK_REQUIRE(stage < pk.num_stages, HK_ERR_INVALID, "commit: no such stage");
         const size_t need = pk.r1cs->l + pk.stage_start[stage + 1];
         const uint64_t* dz = (const uint64_t*)to_device(ctx, ctx->ws_z, z, need * 32, memspace);
@@ -547,9 +609,8 @@ HK_EXPORT int32_t hk_prove(hk_ctx* ctx, uint64_t pk_h, const uint64_t* z, const 
                            const uint64_t* kappas, uint32_t memspace, void* a_affine, void* b_affine, void* c_affine,
                            uint8_t* inf) {
     return guarded(ctx, [&] {
-        auto it = ctx->pks.find(pk_h);
-        HK_REQUIRE(it != ctx->pks.end(), HK_ERR_HANDLE, "unknown pk handle");
-        PkDev& pk = *it->second;
+        auto pksp = find_pk(ctx, pk_h);
+        PkDev& pk = *pksp;
         HK_REQUIRE(z && r && s && a_affine && b_affine && c_affine, HK_ERR_INVALID, "NULL argument");
         HK_REQUIRE(kappas || pk.num_stages == 1, HK_ERR_INVALID, "kappas is NULL");
         const size_t p1 = point_bytes(ctx, 1), p2 = point_bytes(ctx, 2);

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -115,10 +116,28 @@ struct BaseSet {
     size_t n = 0;
     size_t point_bytes = 0;
     void* d = nullptr;      // affine points, AoS
+    // optional window-shifted table (hk_bases_precompute / hk_pk_create):
+    //   tbl[w * n + i] = 2^(tbl_c * w) * P_i   (affine), w < tbl_W.  Trades HBM capacity for the
+    //   removal of the serial window-combination tail and a W-fold smaller bucket set.
+    void* tbl = nullptr;
+    int tbl_c = 0, tbl_W = 0;
+    BaseSet() = default;
+    BaseSet(const BaseSet&) = delete;
+    BaseSet& operator=(const BaseSet&) = delete;
     ~BaseSet() {
         if (d) cudaFree(d);
+        if (tbl) cudaFree(tbl);
     }
 };
+
+// What the MSM pipeline needs to know about a base set.
+struct MsmBases {
+    const void* pts = nullptr;   // affine points
+    size_t n_total = 0;          // points in the set (table row stride)
+    const void* tbl = nullptr;   // window-shifted table or nullptr
+    int c = 0, W = 0;            // table geometry
+};
+inline MsmBases msm_view(const BaseSet& b) { return MsmBases{b.d, b.n, b.tbl, b.tbl_c, b.tbl_W}; }
 
 struct ProfRec {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -131,6 +150,17 @@ struct NttDomain;   // ntt.cu
 struct R1csDev;     // qap.cu
 struct PkDev;       // prove.cu
 
+// Resources shared by a context and its forks (hk_ctx_fork): everything that is uploaded once
+// and then only read by kernels.  Host-side access is serialised by `mu`.
+struct SharedState {
+    std::mutex mu;
+    uint64_t next_handle = 1;
+    std::map<uint64_t, std::shared_ptr<BaseSet>> bases;
+    std::map<uint32_t, std::shared_ptr<NttDomain>> domains;   // by log_n
+    std::map<uint64_t, std::shared_ptr<R1csDev>> r1cs;
+    std::map<uint64_t, std::shared_ptr<PkDev>> pks;
+};
+
 }  // namespace hk
 
 struct hk_ctx {
@@ -140,13 +170,8 @@ struct hk_ctx {
     bool own_stream = false;
     std::string err;
     uint64_t launches = 0;
-    uint64_t next_handle = 1;
     int sm_count = 148;
-
-    std::map<uint64_t, std::unique_ptr<hk::BaseSet>> bases;
-    std::map<uint32_t, std::shared_ptr<hk::NttDomain>> domains;   // by log_n
-    std::map<uint64_t, std::shared_ptr<hk::R1csDev>> r1cs;
-    std::map<uint64_t, std::shared_ptr<hk::PkDev>> pks;
+    std::shared_ptr<hk::SharedState> sh;
 
     // scratch (grow-only; a context is single-threaded by contract)
     hk::DevBuf ws_scalars, ws_hist, ws_items, ws_buckets, ws_chunks, ws_wsum, ws_out, ws_scan;
@@ -231,10 +256,14 @@ inline void prof_end(hk_ctx* ctx, int idx, uint64_t static_units, const uint32_t
 }
 
 // ---- per-module entry points (implemented in the respective .cu files) -----------------
-// msm: bases/scalars are device pointers; out_xyzz receives K XYZZ points (device).
+// msm: sum_{i<n} scalars[i] * bases[offset + i]; scalars are device pointers; out receives K
+// Jacobian points (device).
 template <class Curve, int GROUP>
-void msm_run(hk_ctx* ctx, const void* d_bases, size_t n, const Scalar256* d_scalars, size_t K, bool scalars_mont,
-             void* d_out_jac);
+void msm_run(hk_ctx* ctx, const MsmBases& bases, size_t offset, size_t n, const Scalar256* d_scalars, size_t K,
+             bool scalars_mont, void* d_out_jac);
+// build the window-shifted table of a base set (no-op if present)
+template <class Curve, int GROUP>
+void bases_precompute(hk_ctx* ctx, BaseSet& bs);
 
 template <class Curve>
 void ntt_run(hk_ctx* ctx, uint64_t* d_data, uint32_t log_n, size_t K, uint32_t dir, uint32_t domain);

@@ -12,8 +12,13 @@
 //                      cost the same as uniform ones), interior runs go straight to their
 //                      bucket, the two boundary runs of each segment go to a partial list
 //                      that is folded by k_msm_fold (recursively, same scheme)
-//   5. k_msm_reduce*   per window sum_b b*B_b by chunked running sums, tree sum per window
+//   5. k_msm_reduce*   per window sum_b b*B_b by chunked running sums, then a multi-block tree sum
 //   6. k_msm_combine   Horner over windows -> one Jacobian point
+//
+// Table mode (base sets with a window-shifted table, tbl[w*n+i] = 2^(c w) P_i): every window's
+// digit selects from its own table row, so ALL windows share ONE bucket set: keys are bucket
+// values only, the reduce stage is W times smaller and step 6 has no doublings at all -- the
+// serial tail that dominated capture r01a disappears.  Memory cost: W x the base set (HBM is 180 GB).
 #pragma once
 #include "common.cuh"
 
@@ -25,20 +30,24 @@ struct MsmPlan {
     uint32_t B;  // buckets per window = 2^(c-1)
 };
 
-inline MsmPlan msm_plan(size_t n, int scalar_bits, int group) {
-    // cost model in field multiplications: accumulate 10/pt/window, reduce ~ (2*14 + tail) per bucket
+inline MsmPlan msm_plan_for(int c, int scalar_bits) {
+    return {c, (scalar_bits + 1 + c - 1) / c, 1u << (c - 1)};
+}
+
+inline MsmPlan msm_plan(size_t n, int scalar_bits, bool table) {
+    // cost model in field multiplications: accumulate 10/pt/window, reduce ~45 per bucket
+    // (per window without a table, once with a table)
     double best = 1e300;
     MsmPlan p{4, 0, 0};
-    for (int c = 3; c <= 16; c++) {
-        int W = (scalar_bits + 1 + c - 1) / c;
-        double B = double(1u << (c - 1));
-        double cost = W * (double(n) * 10.0 + B * 45.0);
+    for (int c = 3; c <= (table ? 20 : 16); c++) {
+        MsmPlan q = msm_plan_for(c, scalar_bits);
+        double B = double(q.B);
+        double cost = table ? q.W * double(n) * 10.0 + B * 60.0 : q.W * (double(n) * 10.0 + B * 45.0);
         if (cost < best) {
             best = cost;
-            p = {c, W, 1u << (c - 1)};
+            p = q;
         }
     }
-    (void)group;
     return p;
 }
 
@@ -72,7 +81,10 @@ __global__ void k_scalars_from_mont(const Scalar256* in, Scalar256* out, size_t 
     for (int k = 0; k < 4; k++) out[i].v[k] = x.r.v[k];
 }
 
-static __global__ void k_msm_hist(const Scalar256* sc, size_t n, int c, int W, uint32_t B, uint32_t* hist) {
+// key = w * key_stride + (|d| - 1): key_stride = B without a table (per-window bucket sets),
+// 0 with a table (one shared bucket set).  item index = w * item_stride + i: item_stride = 0
+// without a table, n_total with one (row w of the table).
+static __global__ void k_msm_hist(const Scalar256* sc, size_t n, int c, int W, uint32_t key_stride, uint32_t* hist) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t s[4] = {sc[i].v[0], sc[i].v[1], sc[i].v[2], sc[i].v[3]};
@@ -80,12 +92,12 @@ static __global__ void k_msm_hist(const Scalar256* sc, size_t n, int c, int W, u
     uint32_t carry = 0;
     for (int w = 0; w < W; w++) {
         int d = msm_digit(s, w, c, W, carry);
-        if (d != 0) atomicAdd(&hist[(size_t)w * B + (uint32_t)(abs(d) - 1)], 1u);
+        if (d != 0) atomicAdd(&hist[(size_t)w * key_stride + (uint32_t)(abs(d) - 1)], 1u);
     }
 }
 
-static __global__ void k_msm_scatter(const Scalar256* sc, size_t n, int c, int W, uint32_t B, uint32_t* cursor,
-                              uint32_t* items, uint32_t* keys) {
+static __global__ void k_msm_scatter(const Scalar256* sc, size_t n, int c, int W, uint32_t key_stride,
+                                     uint32_t item_stride, uint32_t* cursor, uint32_t* items, uint32_t* keys) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t s[4] = {sc[i].v[0], sc[i].v[1], sc[i].v[2], sc[i].v[3]};
@@ -94,9 +106,9 @@ static __global__ void k_msm_scatter(const Scalar256* sc, size_t n, int c, int W
     for (int w = 0; w < W; w++) {
         int d = msm_digit(s, w, c, W, carry);
         if (d != 0) {
-            uint32_t key = (uint32_t)w * B + (uint32_t)(abs(d) - 1);
+            uint32_t key = (uint32_t)w * key_stride + (uint32_t)(abs(d) - 1);
             uint32_t pos = atomicAdd(&cursor[key], 1u);
-            items[pos] = ((uint32_t)i << 1) | (d < 0 ? 1u : 0u);
+            items[pos] = (((uint32_t)w * item_stride + (uint32_t)i) << 1) | (d < 0 ? 1u : 0u);
             keys[pos] = key;
         }
     }
@@ -307,14 +319,17 @@ k_msm_reduce_chunks(const XYZZ<F>* __restrict__ buckets, uint32_t B, uint32_t G,
     chunk_out[g] = acc;
 }
 
+// Multi-block tree sum: every block adds 2*TPB consecutive inputs of window blockIdx.y.
 template <class F, int TPB>
 __global__ void __launch_bounds__(TPB)
-k_msm_window_sum(const XYZZ<F>* __restrict__ chunks, uint32_t T, XYZZ<F>* wsum) {
+k_msm_tree_sum(const XYZZ<F>* __restrict__ in, uint32_t m, uint32_t in_stride, XYZZ<F>* out, uint32_t out_stride) {
     extern __shared__ unsigned char smem_raw[];
     XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(smem_raw);
-    uint32_t w = blockIdx.x;
+    const XYZZ<F>* src = in + (size_t)blockIdx.y * in_stride;
+    uint32_t i0 = blockIdx.x * 2 * TPB + threadIdx.x;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t i = threadIdx.x; i < T; i += TPB) acc.add(chunks[(size_t)w * T + i]);
+    if (i0 < m) acc = src[i0];
+    if (i0 + TPB < m) acc.add(src[i0 + TPB]);
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int off = TPB / 2; off > 0; off >>= 1) {
@@ -325,7 +340,22 @@ k_msm_window_sum(const XYZZ<F>* __restrict__ chunks, uint32_t T, XYZZ<F>* wsum) 
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) wsum[w] = sh[0];
+    if (threadIdx.x == 0) out[(size_t)blockIdx.y * out_stride + blockIdx.x] = sh[0];
+}
+
+// tbl[w*n + i] = 2^(c w) * P_i, affine (one inversion per entry; one-off per base set)
+template <class F>
+__global__ void __launch_bounds__(128)
+k_msm_precompute(const Affine<F>* __restrict__ pts, size_t n, int c, int W, Affine<F>* tbl) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = pts[i];
+    tbl[i] = p;
+    XYZZ<F> acc = XYZZ<F>::from_affine(p);
+    for (int w = 1; w < W; w++) {
+        for (int k = 0; k < c; k++) acc = acc.dbl();
+        tbl[(size_t)w * n + i] = acc.to_affine();
+    }
 }
 
 template <class F>
@@ -346,11 +376,33 @@ __global__ void k_set_identity_jac(Jacobian<F>* out, size_t K) {
 }
 
 template <class Curve, int GROUP>
-void msm_run(hk_ctx* ctx, const void* d_bases_v, size_t n, const Scalar256* d_scalars_in, size_t K,
+void bases_precompute(hk_ctx* ctx, BaseSet& bs) {
+    using F = typename GroupFieldT<Curve, GROUP>::F;
+    if (bs.tbl || bs.n == 0) return;
+    MsmPlan pl = msm_plan(bs.n, Curve::FR_BITS, true);
+    HK_REQUIRE((size_t)pl.W * bs.n < (size_t(1) << 31), HK_ERR_UNSUPPORTED, "precompute: windows * n must be < 2^31");
+    void* t = nullptr;
+    cudaError_t e = cudaMalloc(&t, (size_t)pl.W * bs.n * sizeof(Affine<F>) + 256);
+    if (e != cudaSuccess) throw HkError{HK_ERR_NOMEM, std::string("cudaMalloc(window table): ") + cudaGetErrorString(e)};
+    k_msm_precompute<F><<<ceil_div(bs.n, 128), 128, 0, ctx->stream>>>(reinterpret_cast<const Affine<F>*>(bs.d), bs.n, pl.c,
+                                                                     pl.W, reinterpret_cast<Affine<F>*>(t));
+    ctx->launches++;
+    cudaError_t le = cudaGetLastError();
+    if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
+    if (le != cudaSuccess) {
+        cudaFree(t);
+        throw HkError{HK_ERR_CUDA, std::string("k_msm_precompute: ") + cudaGetErrorString(le)};
+    }
+    bs.tbl = t;
+    bs.tbl_c = pl.c;
+    bs.tbl_W = pl.W;
+}
+
+template <class Curve, int GROUP>
+void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Scalar256* d_scalars_in, size_t K,
              bool scalars_mont, void* d_out_jac_v) {
     using F = typename GroupFieldT<Curve, GROUP>::F;
     using Fr = typename Curve::Fr;
-    const Affine<F>* d_bases = reinterpret_cast<const Affine<F>*>(d_bases_v);
     Jacobian<F>* d_out = reinterpret_cast<Jacobian<F>*>(d_out_jac_v);
     cudaStream_t st = ctx->stream;
     if (K == 0) return;
@@ -360,8 +412,15 @@ void msm_run(hk_ctx* ctx, const void* d_bases_v, size_t n, const Scalar256* d_sc
         return;
     }
     HK_REQUIRE(n < (size_t(1) << 31), HK_ERR_UNSUPPORTED, "msm: n must be < 2^31");
-    MsmPlan pl = msm_plan(n, Curve::FR_BITS, GROUP);
-    const size_t nkeys = (size_t)pl.W * pl.B;
+    const bool table = bv.tbl != nullptr;
+    MsmPlan pl = table ? msm_plan_for(bv.c, Curve::FR_BITS) : msm_plan(n, Curve::FR_BITS, false);
+    if (table) HK_REQUIRE(pl.W == bv.W, HK_ERR_INVALID, "msm: window table geometry mismatch");
+    // bases pointer already advanced by `offset`; table rows are n_total apart
+    const Affine<F>* d_bases = reinterpret_cast<const Affine<F>*>(table ? bv.tbl : bv.pts) + offset;
+    const uint32_t key_stride = table ? 0u : pl.B;
+    const uint32_t item_stride = table ? (uint32_t)bv.n_total : 0u;
+    const uint32_t Wred = table ? 1u : (uint32_t)pl.W;        // bucket sets to reduce
+    const size_t nkeys = (size_t)Wred * pl.B;
     const size_t max_items = n * (size_t)pl.W;
     HK_REQUIRE(max_items < (size_t(1) << 32), HK_ERR_UNSUPPORTED, "msm: n * windows must be < 2^32");
     constexpr int S0 = 32;   // level-0 segment length
@@ -380,7 +439,6 @@ void msm_run(hk_ctx* ctx, const void* d_bases_v, size_t n, const Scalar256* d_sc
     uint32_t* keys = items + max_items;
     XYZZ<F>* buckets = ctx->ws_buckets.as<XYZZ<F>>(nkeys);
     const uint32_t nthr0 = ceil_div(max_items, S0);
-    // partial lists: level sizes 2*nthr0, then shrink by S1/2 each level
     std::vector<uint32_t> lvl_in;      // entries consumed at fold level l
     {
         uint32_t cur = 2 * nthr0;
@@ -395,20 +453,27 @@ void msm_run(hk_ctx* ctx, const void* d_bases_v, size_t n, const Scalar256* d_sc
     for (uint32_t v : lvl_in) part_total += v;
     XYZZ<F>* partial = ctx->ws_chunks.as<XYZZ<F>>(part_total);
     uint32_t* partial_keys = ctx->ws_misc.as<uint32_t>(part_total);
-    // reduction geometry
-    uint32_t G = pl.B >= 2048 ? 16 : (pl.B >= 64 ? 4 : 1);
+    // reduction geometry: short serial chunks, then a multi-block tree
+    uint32_t G = pl.B >= 1024 ? 4 : (pl.B >= 64 ? 2 : 1);
     uint32_t T = pl.B / G;
-    XYZZ<F>* chunk_out = ctx->ws_wsum.as<XYZZ<F>>((size_t)T * pl.W + pl.W);
-    XYZZ<F>* wsum = chunk_out + (size_t)T * pl.W;
+    constexpr int TS_TPB = 64;
+    // tree levels: T -> ceil(T / 128) -> ... -> 1 (per window)
+    std::vector<uint32_t> tree;
+    for (uint32_t m = T; m > 1; m = ceil_div(m, 2 * TS_TPB)) tree.push_back(m);
+    size_t tree_total = (size_t)T * Wred;
+    for (uint32_t m : tree) tree_total += (size_t)ceil_div(m, 2 * TS_TPB) * Wred;
+    XYZZ<F>* chunk_out = ctx->ws_wsum.as<XYZZ<F>>(tree_total + Wred);
+    HK_CUDA(cudaFuncSetAttribute(k_msm_tree_sum<F, TS_TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(TS_TPB * sizeof(XYZZ<F>))));
 
     for (size_t k = 0; k < K; k++) {
         const Scalar256* d_sc = d_sc_all + k * n;
         HK_CUDA(cudaMemsetAsync(hist, 0, (nkeys + 4) * sizeof(uint32_t), st));
         HK_CUDA(cudaMemsetAsync(buckets, 0, nkeys * sizeof(XYZZ<F>), st));
-        k_msm_hist<<<ceil_div(n, 256), 256, 0, st>>>(d_sc, n, pl.c, pl.W, pl.B, hist);
+        k_msm_hist<<<ceil_div(n, 256), 256, 0, st>>>(d_sc, n, pl.c, pl.W, key_stride, hist);
         HK_LAUNCH_CHECK(ctx);
         exclusive_scan_u32(ctx, hist, nkeys, d_count);
-        k_msm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(d_sc, n, pl.c, pl.W, pl.B, hist, items, keys);
+        k_msm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(d_sc, n, pl.c, pl.W, key_stride, item_stride, hist, items, keys);
         HK_LAUNCH_CHECK(ctx);
         int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2);
         k_msm_accum<F, S0><<<ceil_div(nthr0, 128), 128, 0, st>>>(d_bases, items, keys, d_count, buckets, partial,
@@ -429,12 +494,21 @@ void msm_run(hk_ctx* ctx, const void* d_bases_v, size_t n, const Scalar256* d_sc
             HK_LAUNCH_CHECK(ctx);
             off += n_in;
         }
-        k_msm_reduce_chunks<F><<<ceil_div((size_t)T * pl.W, 128), 128, 0, st>>>(buckets, pl.B, G, T, pl.W, chunk_out);
+        k_msm_reduce_chunks<F><<<ceil_div((size_t)T * Wred, 128), 128, 0, st>>>(buckets, pl.B, G, T, Wred, chunk_out);
         HK_LAUNCH_CHECK(ctx);
-        constexpr int WS_TPB = 64;
-        k_msm_window_sum<F, WS_TPB><<<pl.W, WS_TPB, WS_TPB * sizeof(XYZZ<F>), st>>>(chunk_out, T, wsum);
-        HK_LAUNCH_CHECK(ctx);
-        k_msm_combine<F><<<1, 32, 0, st>>>(wsum, pl.W, pl.c, d_out + k);
+        XYZZ<F>* cur = chunk_out;
+        uint32_t cur_stride = T;
+        XYZZ<F>* nxt = chunk_out + (size_t)T * Wred;
+        for (uint32_t m : tree) {
+            uint32_t nb = ceil_div(m, 2 * TS_TPB);
+            k_msm_tree_sum<F, TS_TPB><<<dim3(nb, Wred), TS_TPB, TS_TPB * sizeof(XYZZ<F>), st>>>(cur, m, cur_stride, nxt, nb);
+            HK_LAUNCH_CHECK(ctx);
+            cur = nxt;
+            cur_stride = nb;
+            nxt += (size_t)nb * Wred;
+        }
+        // cur: one point per window (stride 1 when the tree ran, T == 1 otherwise)
+        k_msm_combine<F><<<1, 32, 0, st>>>(cur, (int)Wred, pl.c, d_out + k);
         HK_LAUNCH_CHECK(ctx);
     }
 }

@@ -251,8 +251,10 @@ __global__ void k_domain_scalars(typename Curve::Fr* sc, uint32_t log_n) {
 template <class Curve>
 std::shared_ptr<NttDomain> ntt_domain(hk_ctx* ctx, uint32_t log_n) {
     using Fr = typename Curve::Fr;
-    auto it = ctx->domains.find(log_n);
-    if (it != ctx->domains.end()) return it->second;
+    // One builder at a time; forks of a context share the tables (read-only once built).
+    std::lock_guard<std::mutex> lk(ctx->sh->mu);
+    auto it = ctx->sh->domains.find(log_n);
+    if (it != ctx->sh->domains.end()) return it->second;
     HK_REQUIRE(log_n <= (uint32_t)Curve::TWO_ADICITY, HK_ERR_UNSUPPORTED,
                "ntt: log_n exceeds the two-adicity of Fr (PolynomialDegreeTooLarge)");
     HK_REQUIRE(log_n <= 30, HK_ERR_UNSUPPORTED, "ntt: log_n > 30 not supported");
@@ -309,7 +311,8 @@ std::shared_ptr<NttDomain> ntt_domain(hk_ctx* ctx, uint32_t log_n) {
     d->coset_inv_br = coset_inv_br;
     d->n_inv = sc + 4;
     d->zh_inv = sc + 5;
-    ctx->domains[log_n] = d;
+    HK_CUDA(cudaStreamSynchronize(st));   // other streams may use the tables right away
+    ctx->sh->domains[log_n] = d;
     return d;
 }
 

@@ -226,11 +226,21 @@ template void fixed_base_mul<Bls12381, 2>(hk_ctx*, const void*, const Scalar256*
 template void fixed_base_mul<Bn254, 1>(hk_ctx*, const void*, const Scalar256*, size_t, bool, void*);
 template void fixed_base_mul<Bn254, 2>(hk_ctx*, const void*, const Scalar256*, size_t, bool, void*);
 
-static BaseSet& get_bases(hk_ctx* ctx, uint64_t h, int group) {
-    auto it = ctx->bases.find(h);
-    HK_REQUIRE(it != ctx->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
+static std::shared_ptr<BaseSet> get_bases_sp(hk_ctx* ctx, uint64_t h, int group) {
+    std::lock_guard<std::mutex> lk(ctx->sh->mu);
+    auto it = ctx->sh->bases.find(h);
+    HK_REQUIRE(it != ctx->sh->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
     HK_REQUIRE(it->second->group == group, HK_ERR_INVALID, "base set is in the wrong group");
-    return *it->second;
+    return it->second;
+}
+static BaseSet& get_bases(hk_ctx* ctx, uint64_t h, int group) { return *get_bases_sp(ctx, h, group); }
+
+static void alloc_set(BaseSet& bs, int group, size_t n, size_t point_bytes) {
+    bs.group = group;
+    bs.n = n;
+    bs.point_bytes = point_bytes;
+    cudaError_t e = cudaMalloc(&bs.d, n * point_bytes + 256);
+    if (e != cudaSuccess) throw HkError{HK_ERR_NOMEM, std::string("cudaMalloc(pk bases): ") + cudaGetErrorString(e)};
 }
 
 template <class Curve>
@@ -240,9 +250,12 @@ std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d) {
     const size_t P1 = sizeof(Affine<Fq>), P2 = sizeof(Affine<Fq2>);
     auto pk = std::make_shared<PkDev>();
     HK_REQUIRE(d.num_stages >= 1 && d.num_stages <= 8, HK_ERR_INVALID, "pk: num_stages must be 1..8");
-    auto rit = ctx->r1cs.find(d.r1cs);
-    HK_REQUIRE(rit != ctx->r1cs.end(), HK_ERR_HANDLE, "pk: unknown r1cs handle");
-    pk->r1cs = rit->second;
+    {
+        std::lock_guard<std::mutex> lk(ctx->sh->mu);
+        auto rit = ctx->sh->r1cs.find(d.r1cs);
+        HK_REQUIRE(rit != ctx->sh->r1cs.end(), HK_ERR_HANDLE, "pk: unknown r1cs handle");
+        pk->r1cs = rit->second;
+    }
     pk->num_stages = d.num_stages;
     const size_t l = pk->r1cs->l, nw = pk->r1cs->nw, m = l + nw;
     pk->m = m;
@@ -250,7 +263,8 @@ std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d) {
     BaseSet& a_g = get_bases(ctx, d.a_g, 1);
     BaseSet& b_g = get_bases(ctx, d.b_g, 1);
     BaseSet& b_h = get_bases(ctx, d.b_h, 2);
-    BaseSet& h_g = get_bases(ctx, d.h_g, 1);
+    std::shared_ptr<BaseSet> h_g_sp = get_bases_sp(ctx, d.h_g, 1);
+    BaseSet& h_g = *h_g_sp;
     BaseSet& deltas = get_bases(ctx, d.deltas_g, 1);
     HK_REQUIRE(a_g.n == m && b_g.n == m && b_h.n == m, HK_ERR_LENGTH, "pk: a_g/b_g/b_h must have one point per variable");
     HK_REQUIRE(h_g.n == N - 1, HK_ERR_LENGTH, "pk: h_g must have N-1 points (prover.rs:128)");
@@ -264,17 +278,20 @@ std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d) {
         if (bytes) HK_CUDA(cudaMemcpyAsync(dst, src, bytes, k, st));
     };
     // [q[1..m-1], q[0], vk_param, delta]
-    char* a_ext = (char*)pk->a_ext.ensure((m + 2) * P1);
+    alloc_set(pk->a_ext, 1, m + 2, P1);
+    alloc_set(pk->b1_ext, 1, m + 2, P1);
+    alloc_set(pk->b2_ext, 2, m + 2, P2);
+    char* a_ext = (char*)pk->a_ext.d;
     cp(a_ext, (char*)a_g.d + P1, (m - 1) * P1, cudaMemcpyDeviceToDevice);
     cp(a_ext + (m - 1) * P1, a_g.d, P1, cudaMemcpyDeviceToDevice);
     cp(a_ext + m * P1, d.alpha_g, P1, cudaMemcpyHostToDevice);
     cp(a_ext + (m + 1) * P1, (char*)deltas.d + (d.num_stages - 1) * P1, P1, cudaMemcpyDeviceToDevice);
-    char* b1_ext = (char*)pk->b1_ext.ensure((m + 2) * P1);
+    char* b1_ext = (char*)pk->b1_ext.d;
     cp(b1_ext, (char*)b_g.d + P1, (m - 1) * P1, cudaMemcpyDeviceToDevice);
     cp(b1_ext + (m - 1) * P1, b_g.d, P1, cudaMemcpyDeviceToDevice);
     cp(b1_ext + m * P1, d.beta_g, P1, cudaMemcpyHostToDevice);
     cp(b1_ext + (m + 1) * P1, (char*)deltas.d + (d.num_stages - 1) * P1, P1, cudaMemcpyDeviceToDevice);
-    char* b2_ext = (char*)pk->b2_ext.ensure((m + 2) * P2);
+    char* b2_ext = (char*)pk->b2_ext.d;
     cp(b2_ext, (char*)b_h.d + P2, (m - 1) * P2, cudaMemcpyDeviceToDevice);
     cp(b2_ext + (m - 1) * P2, b_h.d, P2, cudaMemcpyDeviceToDevice);
     cp(b2_ext + m * P2, d.beta_h, P2, cudaMemcpyHostToDevice);
@@ -285,16 +302,23 @@ std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d) {
         BaseSet& ck = get_bases(ctx, d.ck[sidx], 1);
         size_t want = pk->stage_start[sidx + 1] - pk->stage_start[sidx];
         HK_REQUIRE(ck.n == want, HK_ERR_LENGTH, "pk: ck[stage] length must equal the stage's witness count");
-        pk->ck_ext.emplace_back(new DevBuf());
+        pk->ck_ext.emplace_back(new BaseSet());
         size_t extra = (sidx + 1 == d.num_stages) ? d.num_stages : 1;
-        char* e = (char*)pk->ck_ext.back()->ensure((ck.n + extra) * P1);
+        alloc_set(*pk->ck_ext.back(), 1, ck.n + extra, P1);
+        char* e = (char*)pk->ck_ext.back()->d;
         cp(e, ck.d, ck.n * P1, cudaMemcpyDeviceToDevice);
         cp(e + ck.n * P1, (char*)deltas.d + (d.num_stages - 1) * P1, P1, cudaMemcpyDeviceToDevice);
         if (extra > 1) cp(e + (ck.n + 1) * P1, deltas.d, (d.num_stages - 1) * P1, cudaMemcpyDeviceToDevice);
     }
-    pk->h_g = h_g.d;
+    pk->h_g = h_g_sp;
     pk->h_g_handle = d.h_g;
     HK_CUDA(cudaStreamSynchronize(st));
+    // window-shifted tables for every base vector of the key (one-off; W x the memory)
+    bases_precompute<Curve, 1>(ctx, pk->a_ext);
+    bases_precompute<Curve, 1>(ctx, pk->b1_ext);
+    bases_precompute<Curve, 2>(ctx, pk->b2_ext);
+    for (auto& ck : pk->ck_ext) bases_precompute<Curve, 1>(ctx, *ck);
+    bases_precompute<Curve, 1>(ctx, *pk->h_g);
     return pk;
 }
 template std::shared_ptr<PkDev> pk_create<Bls12381>(hk_ctx*, const hk_pk_desc&);
@@ -313,7 +337,7 @@ void commit_run(hk_ctx* ctx, PkDev& pk, uint32_t stage, const uint64_t* d_z, con
     k_build_commit_scalars<Fr><<<ceil_div(nw + 1, 256), 256, 0, ctx->stream>>>(w, nw, reinterpret_cast<const Fr*>(d_kappa), sc);
     HK_LAUNCH_CHECK(ctx);
     Jacobian<Fq>* jac = ctx->ws_out.as<Jacobian<Fq>>(8);
-    msm_run<Curve, 1>(ctx, pk.ck_ext[stage]->p, nw + 1, reinterpret_cast<const Scalar256*>(sc), 1, true, jac);
+    msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[stage]), 0, nw + 1, reinterpret_cast<const Scalar256*>(sc), 1, true, jac);
     jac_to_affine<Curve, 1>(ctx, jac, d_out_affine, d_inf, 1);
 }
 template void commit_run<Bls12381>(hk_ctx*, PkDev&, uint32_t, const uint64_t*, const uint64_t*, void*, uint8_t*);
@@ -339,24 +363,25 @@ void prove_run(hk_ctx* ctx, PkDev& pk, const uint64_t* d_z_v, const uint64_t* d_
     Scalar256* S = ctx->ws_io[0].as<Scalar256>(m + 2);
     k_build_abc_scalars<Fr><<<ceil_div(m + 2, 256), 256, 0, st>>>(z, m, r, S);
     HK_LAUNCH_CHECK(ctx);
-    msm_run<Curve, 1>(ctx, pk.a_ext.p, m + 2, S, 1, false, jac + 0);
+    msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, S, 1, false, jac + 0);
     k_patch_scalar<Fr><<<1, 1, 0, st>>>(s, S + m + 1);
     HK_LAUNCH_CHECK(ctx);
-    msm_run<Curve, 1>(ctx, pk.b1_ext.p, m + 2, S, 1, false, jac + 1);
-    msm_run<Curve, 2>(ctx, pk.b2_ext.p, m + 2, S, 1, false, jacB2);
+    msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, S, 1, false, jac + 1);
+    msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, S, 1, false, jacB2);
     // L'
     const size_t nl = pk.stage_start[ns] - pk.stage_start[ns - 1];
     Fr* Ls = ctx->ws_io[1].as<Fr>(nl + ns);
     k_build_l_scalars<Fr><<<ceil_div(nl + ns, 256), 256, 0, st>>>(z + l + pk.stage_start[ns - 1], nl, r, s,
                                                                  reinterpret_cast<const Fr*>(d_kappas), ns - 1, Ls);
     HK_LAUNCH_CHECK(ctx);
-    msm_run<Curve, 1>(ctx, pk.ck_ext[ns - 1]->p, nl + ns, reinterpret_cast<const Scalar256*>(Ls), 1, true, jac + 2);
+    msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[ns - 1]), 0, nl + ns, reinterpret_cast<const Scalar256*>(Ls), 1, true,
+                      jac + 2);
     // h and H
     uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N);
     uint64_t* h = ctx->ws_qap[1].as<uint64_t>(4 * N);
     r1cs_evals<Curve>(ctx, *pk.r1cs, d_z_v, abc);
     qap_h_from_evals<Curve>(ctx, log_n, abc, h);
-    msm_run<Curve, 1>(ctx, pk.h_g, N - 1, reinterpret_cast<const Scalar256*>(h), 1, true, jac + 3);
+    msm_run<Curve, 1>(ctx, msm_view(*pk.h_g), 0, N - 1, reinterpret_cast<const Scalar256*>(h), 1, true, jac + 3);
     k_prove_finish<Curve><<<1, 96, 0, st>>>(jac, jacB2, r, s, reinterpret_cast<Affine<Fq>*>(d_outA),
                                             reinterpret_cast<Affine<Fq2>*>(d_outB),
                                             reinterpret_cast<Affine<Fq>*>(d_outC), d_inf);

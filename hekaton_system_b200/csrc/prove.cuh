@@ -11,9 +11,9 @@ struct PkDev {
     uint32_t num_stages = 0;
     size_t m = 0;                                   // variables incl. the constant one
     std::vector<size_t> stage_start;                // witness-index ranges per stage
-    DevBuf a_ext, b1_ext, b2_ext;                   // [q[1..], q[0], vk_param, delta]
-    std::vector<std::unique_ptr<DevBuf>> ck_ext;    // per stage: [ck.., delta_last (, deltas_g[0..ns-2])]
-    void* h_g = nullptr;                            // borrowed from the h_g base set (must outlive the pk)
+    BaseSet a_ext, b1_ext, b2_ext;                  // [q[1..], q[0], vk_param, delta]  (+ window tables)
+    std::vector<std::unique_ptr<BaseSet>> ck_ext;   // per stage: [ck.., delta_last (, deltas_g[0..ns-2])]
+    std::shared_ptr<BaseSet> h_g;                   // shared with the caller's h_g base set
     uint64_t h_g_handle = 0;
 };
 

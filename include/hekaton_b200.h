@@ -76,6 +76,12 @@ enum { HK_FOP_MUL = 0, HK_FOP_ADD = 1, HK_FOP_SUB = 2, HK_FOP_INV = 3, HK_FOP_TO
 /* ---- context ---------------------------------------------------------------------- */
 /* `stream`: a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create one. */
 int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx** out);
+/* A second context on the same GPU that SHARES the parent's uploaded resources (base sets,
+ * matrices, proving keys, NTT tables -- same handles) but has its own stream and scratch
+ * memory, so independent proofs overlap.  This is the analogue of the reference running several
+ * proofs on separate OS threads against one `ProvingKey` (mpi-snark/src/bin/node.rs:745-795).
+ * Handle-table access is mutex-protected; each context is still single-threaded. */
+int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out);
 int32_t hk_ctx_destroy(hk_ctx* ctx);
 int32_t hk_ctx_sync(hk_ctx* ctx);
 const char* hk_last_error_string(hk_ctx* ctx);
@@ -92,6 +98,10 @@ int32_t hk_bases_upload_g2(hk_ctx* ctx, const void* affine_xy_mont, const uint8_
                            uint32_t memspace, uint64_t* handle);
 int32_t hk_bases_free(hk_ctx* ctx, uint64_t handle);
 int32_t hk_bases_len(hk_ctx* ctx, uint64_t handle, size_t* n);
+/* Build the window-shifted table tbl[w][i] = 2^(c w) * P_i for a base set (W x its memory).  MSMs
+ * on a set with a table use ONE bucket set for all windows and need no final doublings.
+ * hk_pk_create does this for every vector of the key. */
+int32_t hk_bases_precompute(hk_ctx* ctx, uint64_t handle);
 /* Copy points back (affine, Montgomery; infinity as (0,0)); out holds n points. */
 int32_t hk_bases_download(hk_ctx* ctx, uint64_t handle, size_t offset, size_t n, void* out);
 /* Setup helper (generator.rs:128-196 `FixedBase::msm`, restricted to what a synthetic CRS

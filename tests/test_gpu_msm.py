@@ -32,8 +32,9 @@ def _msm_affine(ctx, group, handle, scalars, **kw):
     return dec(aff, cv, inf)[0]
 
 
+@pytest.mark.parametrize("table", [False, True], ids=["plain", "window_table"])
 @pytest.mark.parametrize("group", [1, 2])
-def test_msm_small_and_edges(ctx, group):
+def test_msm_small_and_edges(ctx, group, table):
     cv = ctx.curve
     G = groups(cv.name)[group - 1]
     rng = random.Random(group)
@@ -43,6 +44,8 @@ def test_msm_small_and_edges(ctx, group):
     pts[9] = pts[8]                     # duplicate base  (P + P inside a bucket)
     pts[11] = G.neg(pts[10])            # P and -P        (cancellation inside a bucket)
     h = _upload(ctx, group, pts)
+    if table:
+        ctx.bases_precompute(h)         # window-shifted table: one bucket set, no Horner tail
     uni = [rng.randrange(cv.r) for _ in range(n)]
     same = list(uni)
     same[9] = same[8]
@@ -110,8 +113,9 @@ def test_fixed_base_generation_matches_oracle(ctx):
         ctx.bases_free(h)
 
 
+@pytest.mark.parametrize("table", [False, True], ids=["plain", "window_table"])
 @pytest.mark.parametrize("group,n", [(1, 3000), (1, 40000), (2, 3000)])
-def test_msm_medium_vs_exponent_oracle(ctx, group, n):
+def test_msm_medium_vs_exponent_oracle(ctx, group, n, table):
     """Bases are k_i * G generated on the device (checked above), so the expected result is the
     single scalar multiple (sum k_i s_i) * G -- exact, independent of any MSM algorithm."""
     cv = ctx.curve
@@ -120,6 +124,8 @@ def test_msm_medium_vs_exponent_oracle(ctx, group, n):
     ks = [rng.randrange(1, cv.r) for _ in range(n)]
     enc = codec.g1_affine_to_limbs if group == 1 else codec.g2_affine_to_limbs
     h = ctx.bases_from_scalars(group, enc([G.gen], cv)[0], codec.ints_to_limbs(ks, 4))
+    if table:
+        ctx.bases_precompute(h)
     for kind in ("uniform", "witness_like", "all_same"):
         if kind == "uniform":
             sc = [rng.randrange(cv.r) for _ in range(n)]
@@ -146,3 +152,33 @@ def test_msm_batch(ctx):
     for k in range(K):
         e = sum(a * b for a, b in zip(ks, scs[k])) % cv.r
         assert got[k] == G.mul(G.gen, e)
+
+
+def test_forked_contexts_share_resources(ctx):
+    """hk_ctx_fork: same handles, own stream + scratch; results identical from either context,
+    also when driven from two host threads at once (node.rs:745-795 threading model)."""
+    import threading
+    cv = ctx.curve
+    G = groups(cv.name)[0]
+    rng = random.Random(9)
+    n = 2000
+    ks = [rng.randrange(1, cv.r) for _ in range(n)]
+    h = ctx.bases_from_scalars(1, codec.g1_affine_to_limbs([G.gen], cv)[0], codec.ints_to_limbs(ks, 4))
+    ctx.bases_precompute(h)
+    forks = [ctx.fork() for _ in range(3)]
+    scs = [[rng.randrange(cv.r) for _ in range(n)] for _ in forks]
+    exp = [G.mul(G.gen, sum(a * b for a, b in zip(ks, sc)) % cv.r) for sc in scs]
+    got = [None] * len(forks)
+
+    def work(i):
+        for _ in range(3):
+            got[i] = _msm_affine(forks[i], 1, h, scs[i])
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(forks))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert got == exp
+    assert _msm_affine(ctx, 1, h, scs[0]) == exp[0]
+    for f in forks:
+        f.close()
+    ctx.bases_free(h)
