@@ -20,6 +20,8 @@
 // values only, the reduce stage is W times smaller and step 6 has no doublings at all -- the
 // serial tail that dominated capture r01a disappears.  Memory cost: W x the base set (HBM is 180 GB).
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hk {
@@ -200,8 +202,8 @@ inline void exclusive_scan_u32(hk_ctx* ctx, uint32_t* d, size_t len, uint32_t* d
 // (key = 0xffffffff marks an empty slot).
 static constexpr uint32_t KEY_NONE = 0xffffffffu;
 
-template <class F, int S>
-__global__ void __launch_bounds__(128)
+template <class F, int S, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_msm_accum(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ items,
             const uint32_t* __restrict__ keys, const uint32_t* __restrict__ d_count, XYZZ<F>* buckets,
             XYZZ<F>* partial, uint32_t* partial_keys, uint32_t nthreads) {
@@ -423,7 +425,11 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     const size_t nkeys = (size_t)Wred * pl.B;
     const size_t max_items = n * (size_t)pl.W;
     HK_REQUIRE(max_items < (size_t(1) << 32), HK_ERR_UNSUPPORTED, "msm: n * windows must be < 2^32");
-    constexpr int S0 = 32;   // level-0 segment length
+    // level-0 segment length / occupancy variant (HK_ACCUM_S in {32,64,128}, HK_ACCUM_MINB in {2,3,4};
+    // G2 always uses MINB = 1)
+    static const int env_s = getenv("HK_ACCUM_S") ? atoi(getenv("HK_ACCUM_S")) : 32;
+    static const int env_minb = getenv("HK_ACCUM_MINB") ? atoi(getenv("HK_ACCUM_MINB")) : 2;
+    const int S0 = (env_s == 64 || env_s == 128) ? env_s : 32;
     constexpr int S1 = 16;   // fold segment length
 
     const Scalar256* d_sc_all = d_scalars_in;
@@ -476,8 +482,19 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
         k_msm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(d_sc, n, pl.c, pl.W, key_stride, item_stride, hist, items, keys);
         HK_LAUNCH_CHECK(ctx);
         int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2);
-        k_msm_accum<F, S0><<<ceil_div(nthr0, 128), 128, 0, st>>>(d_bases, items, keys, d_count, buckets, partial,
-                                                               partial_keys, nthr0);
+        {
+            const dim3 grid(ceil_div(nthr0, 128));
+#define HK_ACC(SS, MB) k_msm_accum<F, SS, MB><<<grid, 128, 0, st>>>(d_bases, items, keys, d_count, buckets, partial, partial_keys, nthr0)
+            if constexpr (GROUP == 2) {
+                if (S0 == 32) HK_ACC(32, 1); else if (S0 == 64) HK_ACC(64, 1); else HK_ACC(128, 1);
+            } else {
+                const int mb = env_minb;
+                if (S0 == 32) { if (mb == 3) HK_ACC(32, 3); else if (mb == 4) HK_ACC(32, 4); else HK_ACC(32, 2); }
+                else if (S0 == 64) { if (mb == 3) HK_ACC(64, 3); else if (mb == 4) HK_ACC(64, 4); else HK_ACC(64, 2); }
+                else { if (mb == 3) HK_ACC(128, 3); else if (mb == 4) HK_ACC(128, 4); else HK_ACC(128, 2); }
+            }
+#undef HK_ACC
+        }
         HK_LAUNCH_CHECK(ctx);
         prof_end(ctx, pi, 0, d_count);
         size_t off = 0;

@@ -52,7 +52,9 @@ def main():
             gen1 = codec.g1_affine_to_limbs([cv.g1], cv)[0]
             gen2 = codec.g2_affine_to_limbs([cv.g2], cv)[0]
             rng = np.random.default_rng(1)
-            for group, gen, logs in ((1, gen1, (12, 16, 18, 20, 22)), (2, gen2, (16, 18, 20))):
+            logs1 = tuple(int(x) for x in os.environ.get("HK_PROBE_LOGS1", "12,16,18,20,22").split(",") if x)
+            logs2 = tuple(int(x) for x in os.environ.get("HK_PROBE_LOGS2", "16,18,20").split(",") if x)
+            for group, gen, logs in ((1, gen1, logs1), (2, gen2, logs2)):
                 for lg in logs:
                     n = 1 << lg
                     ks = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
@@ -60,6 +62,8 @@ def main():
                     t0 = time.time()
                     h = ctx.bases_from_scalars(group, gen, ks)
                     t_gen = time.time() - t0
+                    if os.environ.get("HK_PROBE_TABLE", "1") == "1":
+                        ctx.bases_precompute(h)
                     sc = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
                     sc[:, 3] >>= 2
                     d_sc = torch.from_numpy(sc.view(np.int64)).cuda()

@@ -1,0 +1,39 @@
+#!/usr/bin/env python3
+"""Run a few G1 MSMs of 2^LOG points (window-table mode) -- target for ncu captures."""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+import torch
+
+from hekaton_system_b200 import codec
+from hekaton_system_b200.backend import Context
+
+lg = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+group = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+ctx = Context("bls12_381", 0, stream=stream.cuda_stream)
+cv = ctx.curve
+n = 1 << lg
+rng = np.random.default_rng(1)
+ks = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+ks[:, 3] >>= 2
+gen = codec.g1_affine_to_limbs([cv.g1], cv)[0] if group == 1 else codec.g2_affine_to_limbs([cv.g2], cv)[0]
+h = ctx.bases_from_scalars(group, gen, ks)
+if os.environ.get("HK_PROBE_TABLE", "1") == "1":
+    ctx.bases_precompute(h)
+sc = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+sc[:, 3] >>= 2
+d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+d_out = torch.zeros(64, dtype=torch.int64, device="cuda")
+for _ in range(reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ctx.msm(group, h, d_sc.data_ptr(), n=n, out=d_out.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    print(f"msm g{group} 2^{lg}: {e0.elapsed_time(e1):.3f} ms")
+ctx.close()
