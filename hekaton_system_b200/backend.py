@@ -35,7 +35,7 @@ class PkDesc(C.Structure):
         ("a_g", C.c_uint64), ("b_g", C.c_uint64), ("h_g", C.c_uint64), ("b_h", C.c_uint64),
         ("ck", C.c_uint64 * 8), ("num_stages", C.c_uint32), ("deltas_g", C.c_uint64),
         ("alpha_g", C.c_void_p), ("beta_g", C.c_void_p), ("beta_h", C.c_void_p), ("last_delta_h", C.c_void_p),
-        ("r1cs", C.c_uint64), ("stage_start", C.c_uint32 * 9),
+        ("r1cs", C.c_uint64), ("stage_start", C.c_uint32 * 9), ("witness_density_permille", C.c_uint32),
     ]
 
 
@@ -58,7 +58,7 @@ def load_library(path=None):
         "hk_ctx_create": [C.c_int, u32, vp, C.POINTER(vp)],
         "hk_ctx_destroy": [vp],
         "hk_ctx_fork": [vp, vp, C.POINTER(vp)],
-        "hk_bases_precompute": [vp, u64],
+        "hk_bases_precompute": [vp, u64, u32],
         "hk_ctx_sync": [vp],
         "hk_curve_info": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)],
         "hk_bases_upload_g1": [vp, vp, u8p, sz, u32, C.POINTER(u64)],
@@ -218,8 +218,8 @@ class Context:
         self._ck(self.lib.hk_bases_download(self.h, handle, offset, n, out.ctypes.data))
         return out
 
-    def bases_precompute(self, handle):
-        self._ck(self.lib.hk_bases_precompute(self.h, handle))
+    def bases_precompute(self, handle, density=1.0):
+        self._ck(self.lib.hk_bases_precompute(self.h, handle, int(round(density * 1000))))
 
     def bases_free(self, handle):
         self._ck(self.lib.hk_bases_free(self.h, handle))

@@ -389,13 +389,15 @@ HK_EXPORT int32_t hk_bases_len(hk_ctx* ctx, uint64_t handle, size_t* n) {
         *n = find_bases_any(ctx, handle)->n;
     });
 }
-HK_EXPORT int32_t hk_bases_precompute(hk_ctx* ctx, uint64_t handle) {
+HK_EXPORT int32_t hk_bases_precompute(hk_ctx* ctx, uint64_t handle, uint32_t density_permille) {
     return guarded(ctx, [&] {
         auto bs = find_bases_any(ctx, handle);
+        HK_REQUIRE(density_permille <= 1000, HK_ERR_INVALID, "density_permille must be 0..1000");
+        const double dn = density_permille ? density_permille / 1000.0 : 1.0;
         if (bs->group == 1)
-            by_curve(ctx, [&] { bases_precompute<Bls12381, 1>(ctx, *bs); }, [&] { bases_precompute<Bn254, 1>(ctx, *bs); });
+            by_curve(ctx, [&] { bases_precompute<Bls12381, 1>(ctx, *bs, dn); }, [&] { bases_precompute<Bn254, 1>(ctx, *bs, dn); });
         else
-            by_curve(ctx, [&] { bases_precompute<Bls12381, 2>(ctx, *bs); }, [&] { bases_precompute<Bn254, 2>(ctx, *bs); });
+            by_curve(ctx, [&] { bases_precompute<Bls12381, 2>(ctx, *bs, dn); }, [&] { bases_precompute<Bn254, 2>(ctx, *bs, dn); });
     });
 }
 HK_EXPORT int32_t hk_bases_download(hk_ctx* ctx, uint64_t handle, size_t offset, size_t n, void* out) {

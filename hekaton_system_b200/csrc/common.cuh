@@ -261,9 +261,10 @@ inline void prof_end(hk_ctx* ctx, int idx, uint64_t static_units, const uint32_t
 template <class Curve, int GROUP>
 void msm_run(hk_ctx* ctx, const MsmBases& bases, size_t offset, size_t n, const Scalar256* d_scalars, size_t K,
              bool scalars_mont, void* d_out_jac);
-// build the window-shifted table of a base set (no-op if present)
+// build the window-shifted table of a base set (no-op if present); density = expected fraction of
+// full-width scalars (1.0 = uniform), steers the window size
 template <class Curve, int GROUP>
-void bases_precompute(hk_ctx* ctx, BaseSet& bs);
+void bases_precompute(hk_ctx* ctx, BaseSet& bs, double density);
 
 template <class Curve>
 void ntt_run(hk_ctx* ctx, uint64_t* d_data, uint32_t log_n, size_t K, uint32_t dir, uint32_t domain);

@@ -2,5 +2,5 @@
 #include "msm_impl.cuh"
 namespace hk {
 template void msm_run<Bn254, 2>(hk_ctx*, const MsmBases&, size_t, size_t, const Scalar256*, size_t, bool, void*);
-template void bases_precompute<Bn254, 2>(hk_ctx*, BaseSet&);
+template void bases_precompute<Bn254, 2>(hk_ctx*, BaseSet&, double);
 }

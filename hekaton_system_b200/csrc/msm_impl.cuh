@@ -36,15 +36,24 @@ inline MsmPlan msm_plan_for(int c, int scalar_bits) {
     return {c, (scalar_bits + 1 + c - 1) / c, 1u << (c - 1)};
 }
 
-inline MsmPlan msm_plan(size_t n, int scalar_bits, bool table) {
-    // cost model in field multiplications: accumulate 10/pt/window, reduce ~45 per bucket
-    // (per window without a table, once with a table)
+// Window size from a cost model in Fq multiplications, calibrated on B200 (profiles/r01b):
+//   accumulate: 10 per item; items = density * n per window (+ ~n/2 once for 0/1 scalars when
+//               density < 1: a scalar equal to 1 has a single non-zero digit)
+//   reduce:     ~300 per bucket (chunked running sums + chunk offset multiply + tree; these
+//               kernels are latency-bound, far from the multiplier peak), per window without a
+//               table, once with a table
+// `density` = expected fraction of scalars that are "full width" (witness vectors of SHA-256 /
+// Poseidon circuits are mostly bits: SURVEY.md 8d).
+inline MsmPlan msm_plan(size_t n, int scalar_bits, bool table, double density = 1.0) {
     double best = 1e300;
     MsmPlan p{4, 0, 0};
+    if (density <= 0 || density > 1) density = 1.0;
+    const double ones = density < 1.0 ? 0.5 * double(n) : 0.0;
     for (int c = 3; c <= (table ? 20 : 16); c++) {
         MsmPlan q = msm_plan_for(c, scalar_bits);
         double B = double(q.B);
-        double cost = table ? q.W * double(n) * 10.0 + B * 60.0 : q.W * (double(n) * 10.0 + B * 45.0);
+        double acc = 10.0 * (density * double(n) * q.W + ones);
+        double cost = table ? acc + B * 300.0 : acc + q.W * B * 300.0;
         if (cost < best) {
             best = cost;
             p = q;
@@ -378,10 +387,10 @@ __global__ void k_set_identity_jac(Jacobian<F>* out, size_t K) {
 }
 
 template <class Curve, int GROUP>
-void bases_precompute(hk_ctx* ctx, BaseSet& bs) {
+void bases_precompute(hk_ctx* ctx, BaseSet& bs, double density) {
     using F = typename GroupFieldT<Curve, GROUP>::F;
     if (bs.tbl || bs.n == 0) return;
-    MsmPlan pl = msm_plan(bs.n, Curve::FR_BITS, true);
+    MsmPlan pl = msm_plan(bs.n, Curve::FR_BITS, true, density);
     HK_REQUIRE((size_t)pl.W * bs.n < (size_t(1) << 31), HK_ERR_UNSUPPORTED, "precompute: windows * n must be < 2^31");
     void* t = nullptr;
     cudaError_t e = cudaMalloc(&t, (size_t)pl.W * bs.n * sizeof(Affine<F>) + 256);
@@ -460,7 +469,7 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     XYZZ<F>* partial = ctx->ws_chunks.as<XYZZ<F>>(part_total);
     uint32_t* partial_keys = ctx->ws_misc.as<uint32_t>(part_total);
     // reduction geometry: short serial chunks, then a multi-block tree
-    uint32_t G = pl.B >= 1024 ? 4 : (pl.B >= 64 ? 2 : 1);
+    uint32_t G = pl.B >= 32768 ? 8 : (pl.B >= 1024 ? 4 : (pl.B >= 64 ? 2 : 1));
     uint32_t T = pl.B / G;
     constexpr int TS_TPB = 64;
     // tree levels: T -> ceil(T / 128) -> ... -> 1 (per window)
@@ -469,8 +478,7 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     size_t tree_total = (size_t)T * Wred;
     for (uint32_t m : tree) tree_total += (size_t)ceil_div(m, 2 * TS_TPB) * Wred;
     XYZZ<F>* chunk_out = ctx->ws_wsum.as<XYZZ<F>>(tree_total + Wred);
-    HK_CUDA(cudaFuncSetAttribute(k_msm_tree_sum<F, TS_TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(TS_TPB * sizeof(XYZZ<F>))));
+    static_assert(TS_TPB * sizeof(XYZZ<F>) <= 48 * 1024, "tree-sum tile must fit the default dynamic smem limit");
 
     for (size_t k = 0; k < K; k++) {
         const Scalar256* d_sc = d_sc_all + k * n;

@@ -314,11 +314,14 @@ std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d) {
     pk->h_g_handle = d.h_g;
     HK_CUDA(cudaStreamSynchronize(st));
     // window-shifted tables for every base vector of the key (one-off; W x the memory)
-    bases_precompute<Curve, 1>(ctx, pk->a_ext);
-    bases_precompute<Curve, 1>(ctx, pk->b1_ext);
-    bases_precompute<Curve, 2>(ctx, pk->b2_ext);
-    for (auto& ck : pk->ck_ext) bases_precompute<Curve, 1>(ctx, *ck);
-    bases_precompute<Curve, 1>(ctx, *pk->h_g);
+    // The assignment-scalar MSMs (A, B1, B2, L, commitments) see mostly-bit witnesses -> smaller
+    // windows; the H MSM sees uniform scalars.
+    const double wd = d.witness_density_permille ? d.witness_density_permille / 1000.0 : 0.15;
+    bases_precompute<Curve, 1>(ctx, pk->a_ext, wd);
+    bases_precompute<Curve, 1>(ctx, pk->b1_ext, wd);
+    bases_precompute<Curve, 2>(ctx, pk->b2_ext, wd);
+    for (auto& ck : pk->ck_ext) bases_precompute<Curve, 1>(ctx, *ck, wd);
+    bases_precompute<Curve, 1>(ctx, *pk->h_g, 1.0);
     return pk;
 }
 template std::shared_ptr<PkDev> pk_create<Bls12381>(hk_ctx*, const hk_pk_desc&);

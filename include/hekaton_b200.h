@@ -100,8 +100,9 @@ int32_t hk_bases_free(hk_ctx* ctx, uint64_t handle);
 int32_t hk_bases_len(hk_ctx* ctx, uint64_t handle, size_t* n);
 /* Build the window-shifted table tbl[w][i] = 2^(c w) * P_i for a base set (W x its memory).  MSMs
  * on a set with a table use ONE bucket set for all windows and need no final doublings.
- * hk_pk_create does this for every vector of the key. */
-int32_t hk_bases_precompute(hk_ctx* ctx, uint64_t handle);
+ * hk_pk_create does this for every vector of the key.  density_permille (0 = 1000) is the expected
+ * share of full-width scalars and steers the window size: witness vectors are mostly bits. */
+int32_t hk_bases_precompute(hk_ctx* ctx, uint64_t handle, uint32_t density_permille);
 /* Copy points back (affine, Montgomery; infinity as (0,0)); out holds n points. */
 int32_t hk_bases_download(hk_ctx* ctx, uint64_t handle, size_t offset, size_t n, void* out);
 /* Setup helper (generator.rs:128-196 `FixedBase::msm`, restricted to what a synthetic CRS
@@ -175,6 +176,7 @@ typedef struct hk_pk_desc {
     const void* last_delta_h; /* vk.deltas_h.last() (G2 affine, host) */
     uint64_t r1cs;            /* hk_r1cs_upload handle */
     uint32_t stage_start[9];  /* witness index ranges: stage i = [stage_start[i], stage_start[i+1]) */
+    uint32_t witness_density_permille; /* expected share of full-width assignment scalars; 0 = default (150) */
 } hk_pk_desc;
 
 int32_t hk_pk_create(hk_ctx* ctx, const hk_pk_desc* desc, uint64_t* pk_handle);
