@@ -40,8 +40,9 @@ def parse():
     ap.add_argument("--shape", default="big-merkle")
     ap.add_argument("--batch", type=int, default=8, help="subcircuits per GPU per step")
     ap.add_argument("--curve", default="bls12_381")
-    ap.add_argument("--streams", type=int, default=8,
-                    help="proofs in flight per GPU (forked contexts: shared key, own stream + scratch)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="concurrent sub-batches per GPU (forked contexts: shared key, own stream + scratch); "
+                         "each sub-batch of batch/streams proofs is ONE hk_prove_batch pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -168,7 +169,8 @@ def main():
                           f"N=2^{wl.log_n}, {args.curve}, bit-heavy witnesses",
               "subcircuits_per_gpu_per_step": args.batch, "global_batch": args.batch * world,
               "parallelism": f"subcircuits sharded over {world} GPU(s), no data-path collective; "
-                             f"{nstreams} proofs in flight per GPU (forked contexts)",
+                             f"{nstreams} sub-batch(es) of {args.batch // nstreams} proofs in flight per GPU "
+                             f"(hk_prove_batch on forked contexts)",
               "l2": "working set (resident bases ~150 MB + MSM workspaces) exceeds the 126 MB L2",
               "setup_s": round(setup_s, 1)}
 
@@ -201,43 +203,54 @@ def main():
 
     # ------------------------------------------------------------------ device-resident inputs
     dev = torch.device("cuda", local)
-    d_items = []
-    for it in items:
-        dz = torch.from_numpy(it["z"].view(np.int64)).to(dev)
-        drsk = torch.from_numpy(np.concatenate([it["rm"], it["sm"], it["km"][0]]).view(np.int64)).to(dev)
-        out = torch.zeros((2 * P1 + P2 + 8) // 8, dtype=torch.int64, device=dev)
-        d_items.append((dz, drsk, out))
-    flat_n = args.batch * d_items[0][2].numel()
+    assert args.batch % nstreams == 0, "--batch must be a multiple of --streams"
+    per = args.batch // nstreams
+    OUTB = 2 * P1 + P2 + 3
+    chunks = []          # per forked context: contiguous device + host inputs for its sub-batch
+    for t in range(nstreams):
+        its = items[t * per:(t + 1) * per]
+        hz = np.stack([it["z"] for it in its])
+        hr = np.stack([it["rm"] for it in its])
+        hs = np.stack([it["sm"] for it in its])
+        hk_ = np.stack([it["km"] for it in its])
+        dz = torch.from_numpy(hz.view(np.int64)).to(dev)
+        drsk = torch.from_numpy(np.concatenate([hr.ravel(), hs.ravel(), hk_.ravel()]).view(np.int64)).to(dev)
+        out = torch.zeros((per * OUTB + 7) // 8 + 1, dtype=torch.int64, device=dev)
+        chunks.append(dict(hz=hz, hr=hr, hs=hs, hk=hk_, dz=dz, drsk=drsk, out=out))
+    flat_n = sum(ch["out"].numel() for ch in chunks)
     gathered = [torch.zeros(flat_n, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
 
     def step_device():
         # fan out: every worker stream starts after the main stream, the main stream joins them all
         for ws in wstreams[1:]:
             ws.wait_stream(stream)
-        for i, (dz, drsk, out) in enumerate(d_items):
-            p = out.data_ptr()
-            ctxs[i % nstreams].prove_device(pk.handle, dz.data_ptr(), drsk.data_ptr(), drsk.data_ptr() + 32,
-                                            drsk.data_ptr() + 64, p, p + P1, p + P1 + P2, p + 2 * P1 + P2)
+        for t, ch in enumerate(chunks):
+            q = ch["drsk"].data_ptr()
+            p = ch["out"].data_ptr()
+            ctxs[t].prove_batch_device(pk.handle, per, ch["dz"].data_ptr(), q, q + 32 * per, q + 64 * per,
+                                       p, p + per * P1, p + per * (P1 + P2), p + per * (2 * P1 + P2))
         for ws in wstreams[1:]:
             stream.wait_stream(ws)
         if world > 1:
-            dist.all_gather(gathered, torch.cat([o for _, _, o in d_items]))   # proofs to every rank (aggregation input)
+            dist.all_gather(gathered, torch.cat([ch["out"] for ch in chunks]))   # proofs to every rank (aggregation input)
 
     import threading
 
     def step_host():
         # one host thread per context, like the reference's per-proof OS threads (node.rs:745-795);
-        # each call copies its assignment H2D, proves, and copies the proof back
-        res = [None] * len(items)
+        # each call copies its assignments H2D, proves the sub-batch, and copies the proofs back
+        res = [None] * nstreams
 
         def work(t):
-            for i in range(t, len(items), nstreams):
-                it = items[i]
-                res[i] = ctxs[t].prove(pk.handle, it["z"], it["rm"], it["sm"], it["km"])
+            ch = chunks[t]
+            res[t] = ctxs[t].prove_batch(pk.handle, ch["hz"], ch["hr"], ch["hs"], ch["hk"])
 
-        ths = [threading.Thread(target=work, args=(t,)) for t in range(nstreams)]
-        [t.start() for t in ths]
-        [t.join() for t in ths]
+        if nstreams == 1:
+            work(0)
+        else:
+            ths = [threading.Thread(target=work, args=(t,)) for t in range(nstreams)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
         return res
 
     def timed(fn, steps):
@@ -345,7 +358,7 @@ def main():
             "vs_baseline": None, "dtype": "u32x2 (Montgomery Fq/Fr on 32x32+64 IMAD.WIDE lanes)", "data": "synthetic",
             "config": config, "clocks": clocks,
             "e2e": {"value": e2e_v, "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": args.batch * (wl.m * 32 + 96), "d2h_bytes_per_step": args.batch * (2 * P1 + P2 + 3)},
+                    "h2d_bytes_per_step": args.batch * (wl.m * 32 + 96), "d2h_bytes_per_step": args.batch * OUTB},
             "gpu_launches": launches, "roofline": roof, "roofline_ntt": roof_ntt, "cpu_baseline": cpu,
             "verified_vs_trapdoor": verified,
         }

@@ -85,6 +85,7 @@ def load_library(path=None):
         "hk_pk_free": [vp, u64],
         "hk_commit": [vp, u64, u32, u64p, u64p, u32, vp, u8p],
         "hk_prove": [vp, u64, u64p, u64p, u64p, u64p, u32, vp, vp, vp, u8p],
+        "hk_prove_batch": [vp, u64, sz, u64p, u64p, u64p, u64p, u32, vp, vp, vp, u8p],
         "hk_field_op": [vp, u32, u32, u64p, u64p, u64p, sz],
         "hk_bench_field_mul": [vp, u32, u32, u32, C.POINTER(C.c_float)],
         "hk_bench_imad_wide": [vp, u32, C.POINTER(C.c_double)],
@@ -337,6 +338,27 @@ class Context:
                                    kappas.ctypes.data if kappas.size else None, HK_HOST, a.ctypes.data, b.ctypes.data,
                                    c.ctypes.data, inf.ctypes.data))
         return a, b, c, inf
+
+    def prove_batch(self, pk, z, r, s, kappas):
+        """K proofs against one key.  Host arrays: z (K, m, 4), r (K, 4), s (K, 4), kappas (K, ns-1, 4)
+        -> (A (K, 2L), B (K, 4L), C (K, 2L), inf (K, 3))."""
+        z = np.ascontiguousarray(z, dtype=np.uint64)
+        K = z.shape[0]
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(K, 4)
+        s = np.ascontiguousarray(s, dtype=np.uint64).reshape(K, 4)
+        kappas = np.ascontiguousarray(kappas, dtype=np.uint64)
+        a = np.zeros((K, 2 * self.L), dtype=np.uint64)
+        b = np.zeros((K, 4 * self.L), dtype=np.uint64)
+        c = np.zeros((K, 2 * self.L), dtype=np.uint64)
+        inf = np.zeros((K, 3), dtype=np.uint8)
+        self._ck(self.lib.hk_prove_batch(self.h, pk, K, z.ctypes.data, r.ctypes.data, s.ctypes.data,
+                                         kappas.ctypes.data if kappas.size else None, HK_HOST, a.ctypes.data,
+                                         b.ctypes.data, c.ctypes.data, inf.ctypes.data))
+        return a, b, c, inf
+
+    def prove_batch_device(self, pk, K, z, r, s, kappas, a, b, c, inf):
+        """Device pointers (z K*m, r K, s K, kappas K*(ns-1); outputs K each); asynchronous."""
+        self._ck(self.lib.hk_prove_batch(self.h, pk, K, z, r, s, kappas, HK_DEVICE, a, b, c, inf))
 
     def prove_device(self, pk, z, r, s, kappas, a, b, c, inf):
         """All arguments are device pointers; asynchronous on the context stream."""

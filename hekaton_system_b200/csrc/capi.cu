@@ -607,47 +607,62 @@ HK_EXPORT int32_t hk_commit(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, const ui
     });
 }
 
-HK_EXPORT int32_t hk_prove(hk_ctx* ctx, uint64_t pk_h, const uint64_t* z, const uint64_t* r, const uint64_t* s,
-                           const uint64_t* kappas, uint32_t memspace, void* a_affine, void* b_affine, void* c_affine,
-                           uint8_t* inf) {
+HK_EXPORT int32_t hk_prove_batch(hk_ctx* ctx, uint64_t pk_h, size_t K, const uint64_t* z, const uint64_t* r,
+                                 const uint64_t* s, const uint64_t* kappas, uint32_t memspace, void* a_affine,
+                                 void* b_affine, void* c_affine, uint8_t* inf) {
     return guarded(ctx, [&] {
         auto pksp = find_pk(ctx, pk_h);
         PkDev& pk = *pksp;
+        if (K == 0) return;
         HK_REQUIRE(z && r && s && a_affine && b_affine && c_affine, HK_ERR_INVALID, "NULL argument");
         HK_REQUIRE(kappas || pk.num_stages == 1, HK_ERR_INVALID, "kappas is NULL");
         const size_t p1 = point_bytes(ctx, 1), p2 = point_bytes(ctx, 2);
         const uint32_t nk = pk.num_stages - 1;
         if (memspace == HK_DEVICE) {
-            by_curve(ctx, [&] { prove_run<Bls12381>(ctx, pk, z, r, s, kappas, a_affine, b_affine, c_affine, inf); },
-                     [&] { prove_run<Bn254>(ctx, pk, z, r, s, kappas, a_affine, b_affine, c_affine, inf); });
+            HK_REQUIRE(inf, HK_ERR_INVALID, "inf is NULL");
+            by_curve(ctx, [&] { prove_run<Bls12381>(ctx, pk, K, z, r, s, kappas, a_affine, b_affine, c_affine, inf); },
+                     [&] { prove_run<Bn254>(ctx, pk, K, z, r, s, kappas, a_affine, b_affine, c_affine, inf); });
             return;
         }
-        // host staging: z | r | s | kappas in one pinned buffer, one H2D copy
-        const size_t zb = pk.m * 32;
-        const size_t total = zb + 64 + (size_t)nk * 32;
-        char* pin = (char*)ctx->pinned_buf(total + 2 * p1 + p2 + 16);
+        // host staging: [z | r | s | kappas] in one pinned buffer, one H2D copy; one D2H copy back
+        const size_t zb = K * pk.m * 32, rb = K * 32, kb = K * (size_t)nk * 32;
+        const size_t total = zb + 2 * rb + kb;
+        const size_t out_bytes = K * (2 * p1 + p2 + 3);
+        char* pin = (char*)ctx->pinned_buf(total + out_bytes + 64);
         memcpy(pin, z, zb);
-        memcpy(pin + zb, r, 32);
-        memcpy(pin + zb + 32, s, 32);
-        if (nk) memcpy(pin + zb + 64, kappas, (size_t)nk * 32);
+        memcpy(pin + zb, r, rb);
+        memcpy(pin + zb + rb, s, rb);
+        if (kb) memcpy(pin + zb + 2 * rb, kappas, kb);
         char* dz = (char*)ctx->ws_z.ensure(total + 64);
         HK_CUDA(cudaMemcpyAsync(dz, pin, total, cudaMemcpyHostToDevice, ctx->stream));
-        char* d_out = (char*)ctx->ws_io[3].ensure(2 * p1 + p2 + 64);
-        uint8_t* d_inf = (uint8_t*)(d_out + 2 * p1 + p2);
+        char* d_out = (char*)ctx->ws_io[3].ensure(out_bytes + 64);
+        char* dA = d_out;
+        char* dB = dA + K * p1;
+        char* dC = dB + K * p2;
+        uint8_t* d_inf = (uint8_t*)(dC + K * p1);
         const uint64_t* dzz = (const uint64_t*)dz;
         const uint64_t* dr = (const uint64_t*)(dz + zb);
-        const uint64_t* ds = (const uint64_t*)(dz + zb + 32);
-        const uint64_t* dk = (const uint64_t*)(dz + zb + 64);
-        by_curve(ctx, [&] { prove_run<Bls12381>(ctx, pk, dzz, dr, ds, dk, d_out, d_out + p1, d_out + p1 + p2, d_inf); },
-                 [&] { prove_run<Bn254>(ctx, pk, dzz, dr, ds, dk, d_out, d_out + p1, d_out + p1 + p2, d_inf); });
+        const uint64_t* ds = (const uint64_t*)(dz + zb + rb);
+        const uint64_t* dk = (const uint64_t*)(dz + zb + 2 * rb);
+        by_curve(ctx, [&] { prove_run<Bls12381>(ctx, pk, K, dzz, dr, ds, dk, dA, dB, dC, d_inf); },
+                 [&] { prove_run<Bn254>(ctx, pk, K, dzz, dr, ds, dk, dA, dB, dC, d_inf); });
         char* pout = pin + total;
-        HK_CUDA(cudaMemcpyAsync(pout, d_out, 2 * p1 + p2 + 3, cudaMemcpyDeviceToHost, ctx->stream));
+        HK_CUDA(cudaMemcpyAsync(pout, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         HK_CUDA(cudaStreamSynchronize(ctx->stream));
-        memcpy(a_affine, pout, p1);
-        memcpy(b_affine, pout + p1, p2);
-        memcpy(c_affine, pout + p1 + p2, p1);
-        if (inf) memcpy(inf, pout + 2 * p1 + p2, 3);
+        memcpy(a_affine, pout, K * p1);
+        memcpy(b_affine, pout + K * p1, K * p2);
+        memcpy(c_affine, pout + K * (p1 + p2), K * p1);
+        if (inf) memcpy(inf, pout + K * (2 * p1 + p2), K * 3);
     });
+}
+
+HK_EXPORT int32_t hk_prove(hk_ctx* ctx, uint64_t pk_h, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                           const uint64_t* kappas, uint32_t memspace, void* a_affine, void* b_affine, void* c_affine,
+                           uint8_t* inf) {
+    uint8_t scratch[3];
+    if (memspace == HK_DEVICE && !inf) return HK_ERR_INVALID;
+    return hk_prove_batch(ctx, pk_h, 1, z, r, s, kappas, memspace, a_affine, b_affine, c_affine,
+                          inf ? inf : (memspace == HK_DEVICE ? nullptr : scratch));
 }
 
 HK_EXPORT int32_t hk_field_op(hk_ctx* ctx, uint32_t field, uint32_t op, const uint64_t* a, const uint64_t* b,

@@ -256,11 +256,12 @@ inline void prof_end(hk_ctx* ctx, int idx, uint64_t static_units, const uint32_t
 }
 
 // ---- per-module entry points (implemented in the respective .cu files) -----------------
-// msm: sum_{i<n} scalars[i] * bases[offset + i]; scalars are device pointers; out receives K
-// Jacobian points (device).
+// msm: out[k] = sum_{i<n} scalars[k * sc_stride + i] * bases[offset + i] for k < K, in ONE pass (the
+// batch index is an extra bucket-set dimension).  Scalars are device pointers; out receives K
+// Jacobian points (device).  sc_stride = 0 means n.
 template <class Curve, int GROUP>
 void msm_run(hk_ctx* ctx, const MsmBases& bases, size_t offset, size_t n, const Scalar256* d_scalars, size_t K,
-             bool scalars_mont, void* d_out_jac);
+             bool scalars_mont, void* d_out_jac, size_t sc_stride = 0);
 // build the window-shifted table of a base set (no-op if present); density = expected fraction of
 // full-width scalars (1.0 = uniform), steers the window size
 template <class Curve, int GROUP>

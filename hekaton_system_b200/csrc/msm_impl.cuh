@@ -92,32 +92,42 @@ __global__ void k_scalars_from_mont(const Scalar256* in, Scalar256* out, size_t 
     for (int k = 0; k < 4; k++) out[i].v[k] = x.r.v[k];
 }
 
-// key = w * key_stride + (|d| - 1): key_stride = B without a table (per-window bucket sets),
-// 0 with a table (one shared bucket set).  item index = w * item_stride + i: item_stride = 0
-// without a table, n_total with one (row w of the table).
-static __global__ void k_msm_hist(const Scalar256* sc, size_t n, int c, int W, uint32_t key_stride, uint32_t* hist) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t s[4] = {sc[i].v[0], sc[i].v[1], sc[i].v[2], sc[i].v[3]};
+// Bucket sets: one per (vector k, window w) without a table, one per vector k with a table.
+//   key  = (k * sets_per_vec + w * per_window) * B + (|d| - 1)      per_window = 1 / 0
+//   item = w * item_stride + i                                      item_stride = 0 / n_total
+// The K scalar vectors of a batch share the bases, so the batch index is just another bucket-set
+// dimension; `sc_stride` is the distance (in scalars) between consecutive vectors.
+static __global__ void k_msm_hist(const Scalar256* sc, size_t n, size_t K, size_t sc_stride, int c, int W, uint32_t B,
+                                  uint32_t sets_per_vec, uint32_t per_window, uint32_t* hist) {
+    size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= n * K) return;
+    size_t k = g / n, i = g - k * n;
+    const Scalar256* p = sc + k * sc_stride + i;
+    uint64_t s[4] = {p->v[0], p->v[1], p->v[2], p->v[3]};
     if ((s[0] | s[1] | s[2] | s[3]) == 0) return;
     uint32_t carry = 0;
+    const size_t base = k * sets_per_vec;
     for (int w = 0; w < W; w++) {
         int d = msm_digit(s, w, c, W, carry);
-        if (d != 0) atomicAdd(&hist[(size_t)w * key_stride + (uint32_t)(abs(d) - 1)], 1u);
+        if (d != 0) atomicAdd(&hist[(base + (size_t)w * per_window) * B + (uint32_t)(abs(d) - 1)], 1u);
     }
 }
 
-static __global__ void k_msm_scatter(const Scalar256* sc, size_t n, int c, int W, uint32_t key_stride,
-                                     uint32_t item_stride, uint32_t* cursor, uint32_t* items, uint32_t* keys) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t s[4] = {sc[i].v[0], sc[i].v[1], sc[i].v[2], sc[i].v[3]};
+static __global__ void k_msm_scatter(const Scalar256* sc, size_t n, size_t K, size_t sc_stride, int c, int W, uint32_t B,
+                                     uint32_t sets_per_vec, uint32_t per_window, uint32_t item_stride,
+                                     uint32_t* cursor, uint32_t* items, uint32_t* keys) {
+    size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= n * K) return;
+    size_t k = g / n, i = g - k * n;
+    const Scalar256* p = sc + k * sc_stride + i;
+    uint64_t s[4] = {p->v[0], p->v[1], p->v[2], p->v[3]};
     if ((s[0] | s[1] | s[2] | s[3]) == 0) return;
     uint32_t carry = 0;
+    const size_t base = k * sets_per_vec;
     for (int w = 0; w < W; w++) {
         int d = msm_digit(s, w, c, W, carry);
         if (d != 0) {
-            uint32_t key = (uint32_t)w * key_stride + (uint32_t)(abs(d) - 1);
+            uint32_t key = (uint32_t)((base + (size_t)w * per_window) * B) + (uint32_t)(abs(d) - 1);
             uint32_t pos = atomicAdd(&cursor[key], 1u);
             items[pos] = (((uint32_t)w * item_stride + (uint32_t)i) << 1) | (d < 0 ? 1u : 0u);
             keys[pos] = key;
@@ -369,15 +379,17 @@ k_msm_precompute(const Affine<F>* __restrict__ pts, size_t n, int c, int W, Affi
     }
 }
 
+// one block per scalar vector: Horner over its W window sums (W = 1 in table mode: no doublings)
 template <class F>
-__global__ void k_msm_combine(const XYZZ<F>* __restrict__ wsum, int W, int c, Jacobian<F>* out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void k_msm_combine(const XYZZ<F>* __restrict__ wsum_all, int W, int c, Jacobian<F>* out) {
+    if (threadIdx.x != 0) return;
+    const XYZZ<F>* wsum = wsum_all + (size_t)blockIdx.x * W;
     XYZZ<F> acc = wsum[W - 1];
     for (int w = W - 2; w >= 0; w--) {
         for (int k = 0; k < c; k++) acc = acc.dbl();
         acc.add(wsum[w]);
     }
-    *out = Jacobian<F>::from_xyzz(acc);
+    out[blockIdx.x] = Jacobian<F>::from_xyzz(acc);
 }
 
 template <class F>
@@ -411,7 +423,7 @@ void bases_precompute(hk_ctx* ctx, BaseSet& bs, double density) {
 
 template <class Curve, int GROUP>
 void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Scalar256* d_scalars_in, size_t K,
-             bool scalars_mont, void* d_out_jac_v) {
+             bool scalars_mont, void* d_out_jac_v, size_t sc_stride) {
     using F = typename GroupFieldT<Curve, GROUP>::F;
     using Fr = typename Curve::Fr;
     Jacobian<F>* d_out = reinterpret_cast<Jacobian<F>*>(d_out_jac_v);
@@ -422,18 +434,21 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
         HK_LAUNCH_CHECK(ctx);
         return;
     }
+    if (sc_stride == 0) sc_stride = n;
     HK_REQUIRE(n < (size_t(1) << 31), HK_ERR_UNSUPPORTED, "msm: n must be < 2^31");
     const bool table = bv.tbl != nullptr;
     MsmPlan pl = table ? msm_plan_for(bv.c, Curve::FR_BITS) : msm_plan(n, Curve::FR_BITS, false);
     if (table) HK_REQUIRE(pl.W == bv.W, HK_ERR_INVALID, "msm: window table geometry mismatch");
     // bases pointer already advanced by `offset`; table rows are n_total apart
     const Affine<F>* d_bases = reinterpret_cast<const Affine<F>*>(table ? bv.tbl : bv.pts) + offset;
-    const uint32_t key_stride = table ? 0u : pl.B;
+    const uint32_t per_window = table ? 0u : 1u;
     const uint32_t item_stride = table ? (uint32_t)bv.n_total : 0u;
-    const uint32_t Wred = table ? 1u : (uint32_t)pl.W;        // bucket sets to reduce
-    const size_t nkeys = (size_t)Wred * pl.B;
-    const size_t max_items = n * (size_t)pl.W;
-    HK_REQUIRE(max_items < (size_t(1) << 32), HK_ERR_UNSUPPORTED, "msm: n * windows must be < 2^32");
+    const uint32_t Wred = table ? 1u : (uint32_t)pl.W;        // bucket sets per scalar vector
+    const uint32_t nsets = (uint32_t)K * Wred;
+    const size_t nkeys = (size_t)nsets * pl.B;
+    const size_t max_items = n * K * (size_t)pl.W;
+    HK_REQUIRE(nkeys < (size_t(1) << 31), HK_ERR_UNSUPPORTED, "msm: too many buckets for one batch");
+    HK_REQUIRE(max_items < (size_t(1) << 32), HK_ERR_UNSUPPORTED, "msm: batch * n * windows must be < 2^32");
     // level-0 segment length / occupancy variant (HK_ACCUM_S in {32,64,128}, HK_ACCUM_MINB in {2,3,4};
     // G2 always uses MINB = 1)
     static const int env_s = getenv("HK_ACCUM_S") ? atoi(getenv("HK_ACCUM_S")) : 32;
@@ -441,12 +456,21 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     const int S0 = (env_s == 64 || env_s == 128) ? env_s : 32;
     constexpr int S1 = 16;   // fold segment length
 
-    const Scalar256* d_sc_all = d_scalars_in;
+    const Scalar256* d_sc = d_scalars_in;
     if (scalars_mont) {
+        // convert the used part of every vector into a dense K x n array
         Scalar256* conv = ctx->ws_scalars.as<Scalar256>(n * K);
-        k_scalars_from_mont<Fr><<<ceil_div(n * K, 256), 256, 0, st>>>(d_scalars_in, conv, n * K);
-        HK_LAUNCH_CHECK(ctx);
-        d_sc_all = conv;
+        if (sc_stride == n) {
+            k_scalars_from_mont<Fr><<<ceil_div(n * K, 256), 256, 0, st>>>(d_scalars_in, conv, n * K);
+            HK_LAUNCH_CHECK(ctx);
+        } else {
+            for (size_t k = 0; k < K; k++) {
+                k_scalars_from_mont<Fr><<<ceil_div(n, 256), 256, 0, st>>>(d_scalars_in + k * sc_stride, conv + k * n, n);
+                HK_LAUNCH_CHECK(ctx);
+            }
+        }
+        d_sc = conv;
+        sc_stride = n;
     }
     uint32_t* hist = ctx->ws_hist.as<uint32_t>(nkeys + 4);
     uint32_t* d_count = hist + nkeys;     // total item count lives right after the histogram
@@ -472,70 +496,66 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     uint32_t G = pl.B >= 32768 ? 8 : (pl.B >= 1024 ? 4 : (pl.B >= 64 ? 2 : 1));
     uint32_t T = pl.B / G;
     constexpr int TS_TPB = 64;
-    // tree levels: T -> ceil(T / 128) -> ... -> 1 (per window)
-    std::vector<uint32_t> tree;
-    for (uint32_t m = T; m > 1; m = ceil_div(m, 2 * TS_TPB)) tree.push_back(m);
-    size_t tree_total = (size_t)T * Wred;
-    for (uint32_t m : tree) tree_total += (size_t)ceil_div(m, 2 * TS_TPB) * Wred;
-    XYZZ<F>* chunk_out = ctx->ws_wsum.as<XYZZ<F>>(tree_total + Wred);
     static_assert(TS_TPB * sizeof(XYZZ<F>) <= 48 * 1024, "tree-sum tile must fit the default dynamic smem limit");
+    std::vector<uint32_t> tree;        // tree levels: T -> ceil(T / 128) -> ... -> 1 (per bucket set)
+    for (uint32_t m = T; m > 1; m = ceil_div(m, 2 * TS_TPB)) tree.push_back(m);
+    size_t tree_total = (size_t)T * nsets;
+    for (uint32_t m : tree) tree_total += (size_t)ceil_div(m, 2 * TS_TPB) * nsets;
+    XYZZ<F>* chunk_out = ctx->ws_wsum.as<XYZZ<F>>(tree_total + nsets);
 
-    for (size_t k = 0; k < K; k++) {
-        const Scalar256* d_sc = d_sc_all + k * n;
-        HK_CUDA(cudaMemsetAsync(hist, 0, (nkeys + 4) * sizeof(uint32_t), st));
-        HK_CUDA(cudaMemsetAsync(buckets, 0, nkeys * sizeof(XYZZ<F>), st));
-        k_msm_hist<<<ceil_div(n, 256), 256, 0, st>>>(d_sc, n, pl.c, pl.W, key_stride, hist);
-        HK_LAUNCH_CHECK(ctx);
-        exclusive_scan_u32(ctx, hist, nkeys, d_count);
-        k_msm_scatter<<<ceil_div(n, 256), 256, 0, st>>>(d_sc, n, pl.c, pl.W, key_stride, item_stride, hist, items, keys);
-        HK_LAUNCH_CHECK(ctx);
-        int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2);
-        {
-            const dim3 grid(ceil_div(nthr0, 128));
+    HK_CUDA(cudaMemsetAsync(hist, 0, (nkeys + 4) * sizeof(uint32_t), st));
+    HK_CUDA(cudaMemsetAsync(buckets, 0, nkeys * sizeof(XYZZ<F>), st));
+    k_msm_hist<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window, hist);
+    HK_LAUNCH_CHECK(ctx);
+    exclusive_scan_u32(ctx, hist, nkeys, d_count);
+    k_msm_scatter<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window,
+                                                        item_stride, hist, items, keys);
+    HK_LAUNCH_CHECK(ctx);
+    int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2);
+    {
+        const dim3 grid(ceil_div(nthr0, 128));
 #define HK_ACC(SS, MB) k_msm_accum<F, SS, MB><<<grid, 128, 0, st>>>(d_bases, items, keys, d_count, buckets, partial, partial_keys, nthr0)
-            if constexpr (GROUP == 2) {
-                if (S0 == 32) HK_ACC(32, 1); else if (S0 == 64) HK_ACC(64, 1); else HK_ACC(128, 1);
-            } else {
-                const int mb = env_minb;
-                if (S0 == 32) { if (mb == 3) HK_ACC(32, 3); else if (mb == 4) HK_ACC(32, 4); else HK_ACC(32, 2); }
-                else if (S0 == 64) { if (mb == 3) HK_ACC(64, 3); else if (mb == 4) HK_ACC(64, 4); else HK_ACC(64, 2); }
-                else { if (mb == 3) HK_ACC(128, 3); else if (mb == 4) HK_ACC(128, 4); else HK_ACC(128, 2); }
-            }
+        if constexpr (GROUP == 2) {
+            if (S0 == 32) HK_ACC(32, 1); else if (S0 == 64) HK_ACC(64, 1); else HK_ACC(128, 1);
+        } else {
+            const int mb = env_minb;
+            if (S0 == 32) { if (mb == 3) HK_ACC(32, 3); else if (mb == 4) HK_ACC(32, 4); else HK_ACC(32, 2); }
+            else if (S0 == 64) { if (mb == 3) HK_ACC(64, 3); else if (mb == 4) HK_ACC(64, 4); else HK_ACC(64, 2); }
+            else { if (mb == 3) HK_ACC(128, 3); else if (mb == 4) HK_ACC(128, 4); else HK_ACC(128, 2); }
+        }
 #undef HK_ACC
-        }
-        HK_LAUNCH_CHECK(ctx);
-        prof_end(ctx, pi, 0, d_count);
-        size_t off = 0;
-        for (size_t l = 0; l < lvl_in.size(); l++) {
-            uint32_t n_in = lvl_in[l];
-            uint32_t thr = ceil_div(n_in, S1);
-            int final_level = (l + 1 == lvl_in.size());
-            XYZZ<F>* in = partial + off;
-            uint32_t* in_keys = partial_keys + off;
-            XYZZ<F>* out = partial + off + n_in;
-            uint32_t* out_keys = partial_keys + off + n_in;
-            k_msm_fold<F, S1><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr,
-                                                                final_level);
-            HK_LAUNCH_CHECK(ctx);
-            off += n_in;
-        }
-        k_msm_reduce_chunks<F><<<ceil_div((size_t)T * Wred, 128), 128, 0, st>>>(buckets, pl.B, G, T, Wred, chunk_out);
-        HK_LAUNCH_CHECK(ctx);
-        XYZZ<F>* cur = chunk_out;
-        uint32_t cur_stride = T;
-        XYZZ<F>* nxt = chunk_out + (size_t)T * Wred;
-        for (uint32_t m : tree) {
-            uint32_t nb = ceil_div(m, 2 * TS_TPB);
-            k_msm_tree_sum<F, TS_TPB><<<dim3(nb, Wred), TS_TPB, TS_TPB * sizeof(XYZZ<F>), st>>>(cur, m, cur_stride, nxt, nb);
-            HK_LAUNCH_CHECK(ctx);
-            cur = nxt;
-            cur_stride = nb;
-            nxt += (size_t)nb * Wred;
-        }
-        // cur: one point per window (stride 1 when the tree ran, T == 1 otherwise)
-        k_msm_combine<F><<<1, 32, 0, st>>>(cur, (int)Wred, pl.c, d_out + k);
-        HK_LAUNCH_CHECK(ctx);
     }
+    HK_LAUNCH_CHECK(ctx);
+    prof_end(ctx, pi, 0, d_count);
+    size_t off = 0;
+    for (size_t l = 0; l < lvl_in.size(); l++) {
+        uint32_t n_in = lvl_in[l];
+        uint32_t thr = ceil_div(n_in, S1);
+        int final_level = (l + 1 == lvl_in.size());
+        XYZZ<F>* in = partial + off;
+        uint32_t* in_keys = partial_keys + off;
+        XYZZ<F>* out = partial + off + n_in;
+        uint32_t* out_keys = partial_keys + off + n_in;
+        k_msm_fold<F, S1><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
+        HK_LAUNCH_CHECK(ctx);
+        off += n_in;
+    }
+    k_msm_reduce_chunks<F><<<ceil_div((size_t)T * nsets, 128), 128, 0, st>>>(buckets, pl.B, G, T, nsets, chunk_out);
+    HK_LAUNCH_CHECK(ctx);
+    XYZZ<F>* cur = chunk_out;
+    uint32_t cur_stride = T;
+    XYZZ<F>* nxt = chunk_out + (size_t)T * nsets;
+    for (uint32_t m : tree) {
+        uint32_t nb = ceil_div(m, 2 * TS_TPB);
+        k_msm_tree_sum<F, TS_TPB><<<dim3(nb, nsets), TS_TPB, TS_TPB * sizeof(XYZZ<F>), st>>>(cur, m, cur_stride, nxt, nb);
+        HK_LAUNCH_CHECK(ctx);
+        cur = nxt;
+        cur_stride = nb;
+        nxt += (size_t)nb * nsets;
+    }
+    // cur: one point per bucket set, K * Wred of them, vector-major
+    k_msm_combine<F><<<(unsigned)K, 32, 0, st>>>(cur, (int)Wred, pl.c, d_out);
+    HK_LAUNCH_CHECK(ctx);
 }
 
 }  // namespace hk

@@ -96,34 +96,43 @@ k_fixed_base_mul(const XYZZ<F>* __restrict__ tbl, const Scalar256* __restrict__ 
 
 // ---- scalar staging ---------------------------------------------------------------------------
 // S = from_mont([ z[1..m-1], 1, 1, x ])  (m + 2 canonical scalars)
+// blockIdx.y = proof index p in the batch
 template <class Fr>
-__global__ void k_build_abc_scalars(const Fr* __restrict__ z, size_t m, const Fr* x, Scalar256* out) {
+__global__ void k_build_abc_scalars(const Fr* __restrict__ z_all, size_t m, const Fr* x_all, Scalar256* out_all) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= m + 2) return;
+    const size_t p = blockIdx.y;
+    const Fr* z = z_all + p * m;
+    Scalar256* out = out_all + p * (m + 2);
     Fr v;
     if (i < m - 1) v = z[i + 1];
     else if (i < m + 1) v = Fr::one();
-    else v = *x;
+    else v = x_all[p];
     v = v.from_mont();
     for (int k = 0; k < 4; k++) out[i].v[k] = v.r.v[k];
 }
 
+// dst[p * stride] = from_mont(x[p])
 template <class Fr>
-__global__ void k_patch_scalar(const Fr* x, Scalar256* dst) {
-    if (threadIdx.x || blockIdx.x) return;
-    Fr v = (*x).from_mont();
-    for (int k = 0; k < 4; k++) dst->v[k] = v.r.v[k];
+__global__ void k_patch_scalar(const Fr* x, Scalar256* dst, size_t stride, size_t K) {
+    size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (p >= K) return;
+    Fr v = x[p].from_mont();
+    for (int k = 0; k < 4; k++) dst[p * stride].v[k] = v.r.v[k];
 }
 
-// L' scalars (Montgomery): [ w_last (nl), -(r s), -kappa_0 .. -kappa_{ns-2} ]
+// L' scalars (Montgomery), per proof: [ w_last (nl), -(r s), -kappa_0 .. -kappa_{ns-2} ]
 template <class Fr>
-__global__ void k_build_l_scalars(const Fr* __restrict__ w_last, size_t nl, const Fr* r, const Fr* s,
-                                  const Fr* kappas, uint32_t nk, Fr* out) {
+__global__ void k_build_l_scalars(const Fr* __restrict__ z_all, size_t m, size_t w_off, size_t nl, const Fr* r,
+                                  const Fr* s, const Fr* kappas, uint32_t nk, Fr* out_all) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= nl + 1 + nk) return;
+    const size_t p = blockIdx.y;
+    const Fr* w_last = z_all + p * m + w_off;
+    Fr* out = out_all + p * (nl + 1 + nk);
     if (i < nl) out[i] = w_last[i];
-    else if (i == nl) out[i] = ((*r) * (*s)).neg();
-    else out[i] = kappas[i - nl - 1].neg();
+    else if (i == nl) out[i] = (r[p] * s[p]).neg();
+    else out[i] = kappas[p * nk + (i - nl - 1)].neg();
 }
 
 // commit scalars (Montgomery): [ w_stage (nw), kappa ]
@@ -135,15 +144,25 @@ __global__ void k_build_commit_scalars(const Fr* __restrict__ w, size_t nw, cons
 }
 
 // ---- finish -----------------------------------------------------------------------------------
-// jac[0] = A, jac[1] = B1, jac[2] = L', jac[3] = H (G1);  jacB2 (G2);  r, s Montgomery Fr.
+// One block per proof p.  jac = [A x K | B1 x K | L' x K | H x K] (G1);  jacB2 x K (G2);
+// r, s: K Montgomery Fr each.
 template <class Curve>
 __global__ void __launch_bounds__(96)
-k_prove_finish(const Jacobian<typename Curve::Fq>* jac, const Jacobian<typename Curve::Fq2>* jacB2,
-               const typename Curve::Fr* r_m, const typename Curve::Fr* s_m, Affine<typename Curve::Fq>* outA,
-               Affine<typename Curve::Fq2>* outB, Affine<typename Curve::Fq>* outC, uint8_t* inf) {
+k_prove_finish(const Jacobian<typename Curve::Fq>* jac_all, const Jacobian<typename Curve::Fq2>* jacB2_all,
+               const typename Curve::Fr* r_all, const typename Curve::Fr* s_all, Affine<typename Curve::Fq>* outA_all,
+               Affine<typename Curve::Fq2>* outB_all, Affine<typename Curve::Fq>* outC_all, uint8_t* inf_all, uint32_t K) {
     using Fq = typename Curve::Fq;
     using Fq2 = typename Curve::Fq2;
     __shared__ XYZZ<Fq> sh[2];
+    const uint32_t p = blockIdx.x;
+    const Jacobian<Fq> jac[4] = {jac_all[p], jac_all[K + p], jac_all[2 * K + p], jac_all[3 * K + p]};
+    const Jacobian<Fq2>* jacB2 = jacB2_all + p;
+    const typename Curve::Fr* r_m = r_all + p;
+    const typename Curve::Fr* s_m = s_all + p;
+    Affine<Fq>* outA = outA_all + p;
+    Affine<Fq2>* outB = outB_all + p;
+    Affine<Fq>* outC = outC_all + p;
+    uint8_t* inf = inf_all + 3 * p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) {
         if (warp == 0) {
@@ -347,11 +366,12 @@ template void commit_run<Bls12381>(hk_ctx*, PkDev&, uint32_t, const uint64_t*, c
 template void commit_run<Bn254>(hk_ctx*, PkDev&, uint32_t, const uint64_t*, const uint64_t*, void*, uint8_t*);
 
 template <class Curve>
-void prove_run(hk_ctx* ctx, PkDev& pk, const uint64_t* d_z_v, const uint64_t* d_r, const uint64_t* d_s,
+void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const uint64_t* d_r, const uint64_t* d_s,
                const uint64_t* d_kappas, void* d_outA, void* d_outB, void* d_outC, uint8_t* d_inf) {
     using Fr = typename Curve::Fr;
     using Fq = typename Curve::Fq;
     using Fq2 = typename Curve::Fq2;
+    if (K == 0) return;
     const Fr* z = reinterpret_cast<const Fr*>(d_z_v);
     const Fr* r = reinterpret_cast<const Fr*>(d_r);
     const Fr* s = reinterpret_cast<const Fr*>(d_s);
@@ -360,39 +380,41 @@ void prove_run(hk_ctx* ctx, PkDev& pk, const uint64_t* d_z_v, const uint64_t* d_
     const size_t N = size_t(1) << log_n;
     const uint32_t ns = pk.num_stages;
     cudaStream_t st = ctx->stream;
-    Jacobian<Fq>* jac = ctx->ws_out.as<Jacobian<Fq>>(8);          // A, B1, L', H
-    Jacobian<Fq2>* jacB2 = reinterpret_cast<Jacobian<Fq2>*>(jac + 4);
-    // A, B1, B2: shared canonical scalar vector, last entry r then s
-    Scalar256* S = ctx->ws_io[0].as<Scalar256>(m + 2);
-    k_build_abc_scalars<Fr><<<ceil_div(m + 2, 256), 256, 0, st>>>(z, m, r, S);
+    const unsigned Ku = (unsigned)K;
+    Jacobian<Fq>* jac = ctx->ws_out.as<Jacobian<Fq>>(8 * K);        // [A | B1 | L' | H] x K, then B2 x K
+    Jacobian<Fq2>* jacB2 = reinterpret_cast<Jacobian<Fq2>*>(jac + 4 * K);
+    // A, B1, B2: shared canonical scalar vectors (one per proof), last entry r then s
+    Scalar256* S = ctx->ws_io[0].as<Scalar256>(K * (m + 2));
+    k_build_abc_scalars<Fr><<<dim3(ceil_div(m + 2, 256), Ku), 256, 0, st>>>(z, m, r, S);
     HK_LAUNCH_CHECK(ctx);
-    msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, S, 1, false, jac + 0);
-    k_patch_scalar<Fr><<<1, 1, 0, st>>>(s, S + m + 1);
+    msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, S, K, false, jac + 0);
+    k_patch_scalar<Fr><<<ceil_div(K, 64), 64, 0, st>>>(s, S + m + 1, m + 2, K);
     HK_LAUNCH_CHECK(ctx);
-    msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, S, 1, false, jac + 1);
-    msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, S, 1, false, jacB2);
+    msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, S, K, false, jac + K);
+    msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, S, K, false, jacB2);
     // L'
     const size_t nl = pk.stage_start[ns] - pk.stage_start[ns - 1];
-    Fr* Ls = ctx->ws_io[1].as<Fr>(nl + ns);
-    k_build_l_scalars<Fr><<<ceil_div(nl + ns, 256), 256, 0, st>>>(z + l + pk.stage_start[ns - 1], nl, r, s,
-                                                                 reinterpret_cast<const Fr*>(d_kappas), ns - 1, Ls);
+    Fr* Ls = ctx->ws_io[1].as<Fr>(K * (nl + ns));
+    k_build_l_scalars<Fr><<<dim3(ceil_div(nl + ns, 256), Ku), 256, 0, st>>>(
+        z, m, l + pk.stage_start[ns - 1], nl, r, s, reinterpret_cast<const Fr*>(d_kappas), ns - 1, Ls);
     HK_LAUNCH_CHECK(ctx);
-    msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[ns - 1]), 0, nl + ns, reinterpret_cast<const Scalar256*>(Ls), 1, true,
-                      jac + 2);
+    msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[ns - 1]), 0, nl + ns, reinterpret_cast<const Scalar256*>(Ls), K, true,
+                      jac + 2 * K);
     // h and H
-    uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N);
-    uint64_t* h = ctx->ws_qap[1].as<uint64_t>(4 * N);
-    r1cs_evals<Curve>(ctx, *pk.r1cs, d_z_v, abc);
-    qap_h_from_evals<Curve>(ctx, log_n, abc, h);
-    msm_run<Curve, 1>(ctx, msm_view(*pk.h_g), 0, N - 1, reinterpret_cast<const Scalar256*>(h), 1, true, jac + 3);
-    k_prove_finish<Curve><<<1, 96, 0, st>>>(jac, jacB2, r, s, reinterpret_cast<Affine<Fq>*>(d_outA),
-                                            reinterpret_cast<Affine<Fq2>*>(d_outB),
-                                            reinterpret_cast<Affine<Fq>*>(d_outC), d_inf);
+    uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N * K);
+    uint64_t* h = ctx->ws_qap[1].as<uint64_t>(4 * N * K);
+    r1cs_evals<Curve>(ctx, *pk.r1cs, d_z_v, abc, K);
+    qap_h_from_evals<Curve>(ctx, log_n, abc, h, K);
+    msm_run<Curve, 1>(ctx, msm_view(*pk.h_g), 0, N - 1, reinterpret_cast<const Scalar256*>(h), K, true, jac + 3 * K,
+                      /*sc_stride=*/N);
+    k_prove_finish<Curve><<<Ku, 96, 0, st>>>(jac, jacB2, r, s, reinterpret_cast<Affine<Fq>*>(d_outA),
+                                             reinterpret_cast<Affine<Fq2>*>(d_outB),
+                                             reinterpret_cast<Affine<Fq>*>(d_outC), d_inf, Ku);
     HK_LAUNCH_CHECK(ctx);
 }
-template void prove_run<Bls12381>(hk_ctx*, PkDev&, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
-                                  void*, void*, void*, uint8_t*);
-template void prove_run<Bn254>(hk_ctx*, PkDev&, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
-                               void*, void*, void*, uint8_t*);
+template void prove_run<Bls12381>(hk_ctx*, PkDev&, size_t, const uint64_t*, const uint64_t*, const uint64_t*,
+                                  const uint64_t*, void*, void*, void*, uint8_t*);
+template void prove_run<Bn254>(hk_ctx*, PkDev&, size_t, const uint64_t*, const uint64_t*, const uint64_t*,
+                               const uint64_t*, void*, void*, void*, uint8_t*);
 
 }  // namespace hk

@@ -29,8 +29,9 @@ std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d);
 template <class Curve>
 void commit_run(hk_ctx* ctx, PkDev& pk, uint32_t stage, const uint64_t* d_z, const uint64_t* d_kappa,
                 void* d_out_affine, uint8_t* d_inf);
+// K proofs against the same key in one pipeline: z K x m, r/s K, kappas K x (ns-1); outputs K each
 template <class Curve>
-void prove_run(hk_ctx* ctx, PkDev& pk, const uint64_t* d_z, const uint64_t* d_r, const uint64_t* d_s,
+void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z, const uint64_t* d_r, const uint64_t* d_s,
                const uint64_t* d_kappas, void* d_outA, void* d_outB, void* d_outC, uint8_t* d_inf);
 
 }  // namespace hk

@@ -23,10 +23,12 @@ __global__ void k_r1cs_evals(const uint32_t* __restrict__ a_ptr, const uint32_t*
                              const Fr* __restrict__ a_val, const uint32_t* __restrict__ b_ptr,
                              const uint32_t* __restrict__ b_col, const Fr* __restrict__ b_val,
                              const uint32_t* __restrict__ c_ptr, const uint32_t* __restrict__ c_col,
-                             const Fr* __restrict__ c_val, const Fr* __restrict__ z, uint32_t n, uint32_t l,
-                             uint32_t N, Fr* abc) {
+                             const Fr* __restrict__ c_val, const Fr* __restrict__ z_all, uint32_t n, uint32_t l,
+                             uint32_t N, Fr* abc_all, size_t m) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    const Fr* z = z_all + (size_t)blockIdx.y * m;              // blockIdx.y = proof index in the batch
+    Fr* abc = abc_all + (size_t)blockIdx.y * 3 * N;
     Fr a = Fr::zero(), b = Fr::zero(), c = Fr::zero();
     if (i < n) {
         for (uint32_t k = a_ptr[i]; k < a_ptr[i + 1]; k++) a = a + a_val[k] * z[a_col[k]];
@@ -41,51 +43,57 @@ __global__ void k_r1cs_evals(const uint32_t* __restrict__ a_ptr, const uint32_t*
 }
 
 template <class Fr>
-__global__ void k_qap_pointwise(Fr* abc, uint32_t N, const Fr* zh_inv) {
+__global__ void k_qap_pointwise(const Fr* abc_all, uint32_t N, const Fr* zh_inv, Fr* out_all) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    const Fr* abc = abc_all + (size_t)blockIdx.y * 3 * N;
     Fr zi = *zh_inv;
     Fr a = abc[i], b = abc[(size_t)N + i], c = abc[2 * (size_t)N + i];
-    abc[i] = (a * b - c) * zi;
+    out_all[(size_t)blockIdx.y * N + i] = (a * b - c) * zi;
 }
 
+// abc: K x [a | b | c] (each N), clobbered; h: K x N.
 template <class Curve>
-void qap_h_from_evals(hk_ctx* ctx, uint32_t log_n, uint64_t* d_abc_v, uint64_t* d_h_v) {
+void qap_h_from_evals(hk_ctx* ctx, uint32_t log_n, uint64_t* d_abc_v, uint64_t* d_h_v, size_t K) {
     using Fr = typename Curve::Fr;
     Fr* abc = reinterpret_cast<Fr*>(d_abc_v);
     Fr* h = reinterpret_cast<Fr*>(d_h_v);
     const size_t N = size_t(1) << log_n;
     HK_REQUIRE(log_n >= 1, HK_ERR_UNSUPPORTED, "qap_h: log_n must be >= 1");
+    if (K == 0) return;
     auto dom = ntt_domain<Curve>(ctx, log_n);
-    Fr* tmp = ctx->ws_ntt_tmp.as<Fr>(3 * N);
-    // 3x ifft (unnormalised, bit-reversed output), in place
-    ntt_passes<Curve>(ctx, *dom, false, true, abc, abc, tmp, 3, false, false, nullptr, nullptr, nullptr);
-    // 3x coset fft from bit-reversed coefficients; scale g^rev(p)/N folded into the load
-    ntt_passes<Curve>(ctx, *dom, true, false, abc, abc, tmp, 3, false, false,
+    Fr* tmp = ctx->ws_ntt_tmp.as<Fr>((3 + 1) * K * N);
+    Fr* ab = tmp + 3 * K * N;      // pointwise result, K x N, contiguous for the batched last transform
+    // 3K x ifft (unnormalised, bit-reversed output), in place
+    ntt_passes<Curve>(ctx, *dom, false, true, abc, abc, tmp, 3 * K, false, false, nullptr, nullptr, nullptr);
+    // 3K x coset fft from bit-reversed coefficients; scale g^rev(p)/N folded into the load
+    ntt_passes<Curve>(ctx, *dom, true, false, abc, abc, tmp, 3 * K, false, false,
                       reinterpret_cast<const Fr*>(dom->coset_br), nullptr, nullptr);
-    k_qap_pointwise<Fr><<<ceil_div(N, 256), 256, 0, ctx->stream>>>(abc, (uint32_t)N,
-                                                                   reinterpret_cast<const Fr*>(dom->zh_inv));
+    k_qap_pointwise<Fr><<<dim3(ceil_div(N, 256), (unsigned)K), 256, 0, ctx->stream>>>(
+        abc, (uint32_t)N, reinterpret_cast<const Fr*>(dom->zh_inv), ab);
     HK_LAUNCH_CHECK(ctx);
-    // coset ifft: DIF(w^-1), last pass scales by g^-j/N (indexed by destination j) and un-permutes
-    ntt_passes<Curve>(ctx, *dom, false, true, abc, h, tmp, 1, false, true, nullptr,
+    // K x coset ifft: DIF(w^-1), last pass scales by g^-j/N (indexed by destination j) and un-permutes
+    ntt_passes<Curve>(ctx, *dom, false, true, ab, h, tmp, K, false, true, nullptr,
                       reinterpret_cast<const Fr*>(dom->coset_inv_nat), nullptr, /*src_clobber_ok=*/true);
 }
 
+// z: K assignments of (l + nw) elements; abc: K x 3N
 template <class Curve>
-void r1cs_evals(hk_ctx* ctx, const R1csDev& m, const uint64_t* d_z, uint64_t* d_abc) {
+void r1cs_evals(hk_ctx* ctx, const R1csDev& m, const uint64_t* d_z, uint64_t* d_abc, size_t K) {
     using Fr = typename Curve::Fr;
     const uint32_t N = 1u << m.log_n;
-    k_r1cs_evals<Fr><<<ceil_div(N, 128), 128, 0, ctx->stream>>>(
+    if (K == 0) return;
+    k_r1cs_evals<Fr><<<dim3(ceil_div(N, 128), (unsigned)K), 128, 0, ctx->stream>>>(
         m.ptr[0], m.col[0], reinterpret_cast<const Fr*>(m.val[0]), m.ptr[1], m.col[1],
         reinterpret_cast<const Fr*>(m.val[1]), m.ptr[2], m.col[2], reinterpret_cast<const Fr*>(m.val[2]),
-        reinterpret_cast<const Fr*>(d_z), (uint32_t)m.n, (uint32_t)m.l, N, reinterpret_cast<Fr*>(d_abc));
+        reinterpret_cast<const Fr*>(d_z), (uint32_t)m.n, (uint32_t)m.l, N, reinterpret_cast<Fr*>(d_abc), m.l + m.nw);
     HK_LAUNCH_CHECK(ctx);
 }
 
-template void qap_h_from_evals<Bls12381>(hk_ctx*, uint32_t, uint64_t*, uint64_t*);
-template void qap_h_from_evals<Bn254>(hk_ctx*, uint32_t, uint64_t*, uint64_t*);
-template void r1cs_evals<Bls12381>(hk_ctx*, const R1csDev&, const uint64_t*, uint64_t*);
-template void r1cs_evals<Bn254>(hk_ctx*, const R1csDev&, const uint64_t*, uint64_t*);
+template void qap_h_from_evals<Bls12381>(hk_ctx*, uint32_t, uint64_t*, uint64_t*, size_t);
+template void qap_h_from_evals<Bn254>(hk_ctx*, uint32_t, uint64_t*, uint64_t*, size_t);
+template void r1cs_evals<Bls12381>(hk_ctx*, const R1csDev&, const uint64_t*, uint64_t*, size_t);
+template void r1cs_evals<Bn254>(hk_ctx*, const R1csDev&, const uint64_t*, uint64_t*, size_t);
 
 std::shared_ptr<R1csDev> r1cs_upload(hk_ctx* ctx, size_t n, size_t l, size_t nw, const uint32_t* const ptr[3],
                                      const uint32_t* const col[3], const uint64_t* const val[3]) {

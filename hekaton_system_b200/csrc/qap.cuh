@@ -17,12 +17,12 @@ struct R1csDev {
 std::shared_ptr<R1csDev> r1cs_upload(hk_ctx* ctx, size_t n, size_t l, size_t nw, const uint32_t* const ptr[3],
                                      const uint32_t* const col[3], const uint64_t* const val[3]);
 
-// abc: device buffer of 3N Fr (a | b | c), clobbered; h: device buffer of N Fr.
+// abc: device buffer of K x 3N Fr (a | b | c per proof), clobbered; h: device buffer of K x N Fr.
 template <class Curve>
-void qap_h_from_evals(hk_ctx* ctx, uint32_t log_n, uint64_t* d_abc, uint64_t* d_h);
+void qap_h_from_evals(hk_ctx* ctx, uint32_t log_n, uint64_t* d_abc, uint64_t* d_h, size_t K = 1);
 
-// abc[0..N) = a evals, [N..2N) = b, [2N..3N) = c from the CSR matrices and z (device, Montgomery).
+// per proof k: abc[k][0..N) = a evals, [N..2N) = b, [2N..3N) = c from the CSR matrices and z[k].
 template <class Curve>
-void r1cs_evals(hk_ctx* ctx, const R1csDev& m, const uint64_t* d_z, uint64_t* d_abc);
+void r1cs_evals(hk_ctx* ctx, const R1csDev& m, const uint64_t* d_z, uint64_t* d_abc, size_t K = 1);
 
 }  // namespace hk

@@ -193,6 +193,15 @@ int32_t hk_prove(hk_ctx* ctx, uint64_t pk, const uint64_t* z, const uint64_t* r,
                  const uint64_t* kappas, uint32_t memspace, void* a_affine, void* b_affine, void* c_affine,
                  uint8_t* inf);
 
+/* K proofs against the SAME proving key in one device pipeline (same-shape subcircuits share a key:
+ * big-merkle has 5 shapes, VKD 7, VM 2 -- tree_hash_circuit.rs:192-216).  Every MSM of the batch runs
+ * as one pass in which the proof index is one more bucket-set dimension, so the latency-bound
+ * reduction stages are paid once per batch.  z: K x m, r, s: K, kappas: K x (num_stages-1), all
+ * Montgomery Fr; outputs: K x A, K x B, K x C (affine, Montgomery), inf: K x 3 bytes. */
+int32_t hk_prove_batch(hk_ctx* ctx, uint64_t pk, size_t K, const uint64_t* z, const uint64_t* r, const uint64_t* s,
+                       const uint64_t* kappas, uint32_t memspace, void* a_affine, void* b_affine, void* c_affine,
+                       uint8_t* inf);
+
 /* ---- test / measurement hooks ------------------------------------------------------- */
 /* Element-wise field op on n elements (host pointers): out[i] = a[i] (op) b[i]. */
 int32_t hk_field_op(hk_ctx* ctx, uint32_t field, uint32_t op, const uint64_t* a, const uint64_t* b,
