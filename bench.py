@@ -149,6 +149,7 @@ def main():
 
     from hekaton_system_b200 import codec, workload
     from hekaton_system_b200.backend import Context
+    from hekaton_system_b200.shard import gather_records, shard_range
 
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
@@ -217,8 +218,8 @@ def main():
         drsk = torch.from_numpy(np.concatenate([hr.ravel(), hs.ravel(), hk_.ravel()]).view(np.int64)).to(dev)
         out = torch.zeros((per * OUTB + 7) // 8 + 1, dtype=torch.int64, device=dev)
         chunks.append(dict(hz=hz, hr=hr, hs=hs, hk=hk_, dz=dz, drsk=drsk, out=out))
-    flat_n = sum(ch["out"].numel() for ch in chunks)
-    gathered = [torch.zeros(flat_n, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+    my_subcircuits = shard_range(args.batch * world, world, rank)      # contiguous chunk per rank (node.rs:471-493)
+    assert len(my_subcircuits) == args.batch
 
     def step_device():
         # fan out: every worker stream starts after the main stream, the main stream joins them all
@@ -232,7 +233,8 @@ def main():
         for ws in wstreams[1:]:
             stream.wait_stream(ws)
         if world > 1:
-            dist.all_gather(gathered, torch.cat([ch["out"] for ch in chunks]))   # proofs to every rank (aggregation input)
+            # the path's one exchange step: proof records to every rank (aggregation input)
+            gather_records(torch.cat([ch["out"] for ch in chunks]).view(1, -1), world)
 
     import threading
 
