@@ -260,3 +260,38 @@ class _StagedView:
 
     def csr(self):
         return self.wl.csr
+
+
+def dump_workload(wl, path, subs):
+    """Write the binary workload file read by host/hk_node.cpp (the C++ `node work`-style driver).
+    subs: list of dicts with Montgomery limb arrays z (m,4), kappa, r, s (4,) and the expected
+    outputs D, A (2L), B (4L), C (2L)."""
+    cv = wl.curve
+    r = cv.r
+    td, ks = wl.trapdoor, wl.key_scalars
+    u64 = lambda *v: np.array(v, dtype="<u8").tobytes()
+    enc = lambda vals, g: codec.ints_to_limbs([v * g % r for v in vals], 4).tobytes()
+    with open(path, "wb") as f:
+        f.write(u64(0x314c574b48, cv.cid, wl.n, wl.l, wl.nw, len(wl.stage_start) - 1))
+        f.write(np.array(wl.stage_start, dtype="<u8").tobytes())
+        for ptr, col, val in wl.csr:
+            f.write(u64(len(col)))
+            f.write(np.ascontiguousarray(ptr, dtype="<u4").tobytes())
+            f.write(np.ascontiguousarray(col, dtype="<u4").tobytes())
+            f.write(np.ascontiguousarray(val, dtype="<u8").tobytes())
+        f.write(codec.g1_affine_to_limbs([cv.g1], cv)[0].tobytes())
+        f.write(codec.g2_affine_to_limbs([cv.g2], cv)[0].tobytes())
+        g1s, g2s = td["g1"], td["g2"]
+        f.write(enc(ks["a_g"], g1s))
+        f.write(enc(ks["b_g"], g1s))
+        f.write(enc(ks["b_g"], g2s))
+        f.write(enc(ks["h_g"], g1s))
+        for v in ks["ck"]:
+            f.write(enc(v, g1s))
+        f.write(enc(ks["deltas"], g1s))
+        f.write(enc([ks["alpha"], ks["beta"]], g1s))
+        f.write(enc([ks["beta"], ks["deltas"][-1]], g2s))
+        f.write(u64(len(subs)))
+        for s in subs:
+            for k in ("z", "kappa", "r", "s", "D", "A", "B", "C"):
+                f.write(np.ascontiguousarray(s[k], dtype="<u8").tobytes())
