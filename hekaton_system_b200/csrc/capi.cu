@@ -273,6 +273,12 @@ float time_ms(hk_ctx* ctx, Fn&& fn) {
 }  // namespace
 
 // ==================================================================================================
+static int32_t ctx_make_side(hk_ctx* ctx) {
+    if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) return HK_ERR_CUDA;
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
+    if (cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
+    return HK_OK;
+}
 HK_EXPORT int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx** out) {
     if (!out) return HK_ERR_INVALID;
     *out = nullptr;
@@ -304,6 +310,10 @@ HK_EXPORT int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx
         }
         ctx->own_stream = true;
     }
+    if (ctx_make_side(ctx) != HK_OK) {
+        delete ctx;
+        return HK_ERR_CUDA;
+    }
     *out = ctx;
     return HK_OK;
 }
@@ -316,6 +326,12 @@ HK_EXPORT int32_t hk_ctx_destroy(hk_ctx* ctx) {
     if (ctx->prof_pinned) cudaFreeHost(ctx->prof_pinned);
     ctx->sh.reset();     // shared resources are freed with the last context that references them
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->side) {
+        cudaStreamSynchronize(ctx->side);
+        cudaStreamDestroy(ctx->side);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HK_OK;
@@ -342,6 +358,10 @@ HK_EXPORT int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out) {
             return HK_ERR_CUDA;
         }
         ctx->own_stream = true;
+    }
+    if (ctx_make_side(ctx) != HK_OK) {
+        delete ctx;
+        return HK_ERR_CUDA;
     }
     *out = ctx;
     return HK_OK;

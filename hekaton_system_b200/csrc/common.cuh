@@ -121,12 +121,14 @@ struct BaseSet {
     //   removal of the serial window-combination tail and a W-fold smaller bucket set.
     void* tbl = nullptr;
     int tbl_c = 0, tbl_W = 0;
+    uint8_t* skip = nullptr;   // 1 byte per point: base is the point at infinity (built with the table)
     BaseSet() = default;
     BaseSet(const BaseSet&) = delete;
     BaseSet& operator=(const BaseSet&) = delete;
     ~BaseSet() {
         if (d) cudaFree(d);
         if (tbl) cudaFree(tbl);
+        if (skip) cudaFree(skip);
     }
 };
 
@@ -136,8 +138,9 @@ struct MsmBases {
     size_t n_total = 0;          // points in the set (table row stride)
     const void* tbl = nullptr;   // window-shifted table or nullptr
     int c = 0, W = 0;            // table geometry
+    const uint8_t* skip = nullptr;   // per-point "is infinity" flags or nullptr
 };
-inline MsmBases msm_view(const BaseSet& b) { return MsmBases{b.d, b.n, b.tbl, b.tbl_c, b.tbl_W}; }
+inline MsmBases msm_view(const BaseSet& b) { return MsmBases{b.d, b.n, b.tbl, b.tbl_c, b.tbl_W, b.skip}; }
 
 struct ProfRec {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -168,6 +171,8 @@ struct hk_ctx {
     uint32_t curve = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t side = nullptr;          // helper stream for work that overlaps the main pipeline
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;

@@ -98,10 +98,12 @@ __global__ void k_scalars_from_mont(const Scalar256* in, Scalar256* out, size_t 
 // The K scalar vectors of a batch share the bases, so the batch index is just another bucket-set
 // dimension; `sc_stride` is the distance (in scalars) between consecutive vectors.
 static __global__ void k_msm_hist(const Scalar256* sc, size_t n, size_t K, size_t sc_stride, int c, int W, uint32_t B,
-                                  uint32_t sets_per_vec, uint32_t per_window, uint32_t* hist) {
+                                  uint32_t sets_per_vec, uint32_t per_window, const uint8_t* __restrict__ skip,
+                                  uint32_t* hist) {
     size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= n * K) return;
     size_t k = g / n, i = g - k * n;
+    if (skip && skip[i]) return;          // base at infinity contributes nothing
     const Scalar256* p = sc + k * sc_stride + i;
     uint64_t s[4] = {p->v[0], p->v[1], p->v[2], p->v[3]};
     if ((s[0] | s[1] | s[2] | s[3]) == 0) return;
@@ -115,10 +117,12 @@ static __global__ void k_msm_hist(const Scalar256* sc, size_t n, size_t K, size_
 
 static __global__ void k_msm_scatter(const Scalar256* sc, size_t n, size_t K, size_t sc_stride, int c, int W, uint32_t B,
                                      uint32_t sets_per_vec, uint32_t per_window, uint32_t item_stride,
-                                     uint32_t* cursor, uint32_t* items, uint32_t* keys) {
+                                     const uint8_t* __restrict__ skip, uint32_t* cursor, uint32_t* items,
+                                     uint32_t* keys) {
     size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= n * K) return;
     size_t k = g / n, i = g - k * n;
+    if (skip && skip[i]) return;
     const Scalar256* p = sc + k * sc_stride + i;
     uint64_t s[4] = {p->v[0], p->v[1], p->v[2], p->v[3]};
     if ((s[0] | s[1] | s[2] | s[3]) == 0) return;
@@ -367,11 +371,12 @@ k_msm_tree_sum(const XYZZ<F>* __restrict__ in, uint32_t m, uint32_t in_stride, X
 // tbl[w*n + i] = 2^(c w) * P_i, affine (one inversion per entry; one-off per base set)
 template <class F>
 __global__ void __launch_bounds__(128)
-k_msm_precompute(const Affine<F>* __restrict__ pts, size_t n, int c, int W, Affine<F>* tbl) {
+k_msm_precompute(const Affine<F>* __restrict__ pts, size_t n, int c, int W, Affine<F>* tbl, uint8_t* skip) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     Affine<F> p = pts[i];
     tbl[i] = p;
+    skip[i] = p.is_inf() ? 1 : 0;
     XYZZ<F> acc = XYZZ<F>::from_affine(p);
     for (int w = 1; w < W; w++) {
         for (int k = 0; k < c; k++) acc = acc.dbl();
@@ -405,17 +410,24 @@ void bases_precompute(hk_ctx* ctx, BaseSet& bs, double density) {
     MsmPlan pl = msm_plan(bs.n, Curve::FR_BITS, true, density);
     HK_REQUIRE((size_t)pl.W * bs.n < (size_t(1) << 31), HK_ERR_UNSUPPORTED, "precompute: windows * n must be < 2^31");
     void* t = nullptr;
+    uint8_t* sk = nullptr;
     cudaError_t e = cudaMalloc(&t, (size_t)pl.W * bs.n * sizeof(Affine<F>) + 256);
-    if (e != cudaSuccess) throw HkError{HK_ERR_NOMEM, std::string("cudaMalloc(window table): ") + cudaGetErrorString(e)};
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sk, bs.n + 256);
+    if (e != cudaSuccess) {
+        if (t) cudaFree(t);
+        throw HkError{HK_ERR_NOMEM, std::string("cudaMalloc(window table): ") + cudaGetErrorString(e)};
+    }
     k_msm_precompute<F><<<ceil_div(bs.n, 128), 128, 0, ctx->stream>>>(reinterpret_cast<const Affine<F>*>(bs.d), bs.n, pl.c,
-                                                                     pl.W, reinterpret_cast<Affine<F>*>(t));
+                                                                     pl.W, reinterpret_cast<Affine<F>*>(t), sk);
     ctx->launches++;
     cudaError_t le = cudaGetLastError();
     if (le == cudaSuccess) le = cudaStreamSynchronize(ctx->stream);
     if (le != cudaSuccess) {
         cudaFree(t);
+        cudaFree(sk);
         throw HkError{HK_ERR_CUDA, std::string("k_msm_precompute: ") + cudaGetErrorString(le)};
     }
+    bs.skip = sk;
     bs.tbl = t;
     bs.tbl_c = pl.c;
     bs.tbl_W = pl.W;
@@ -505,11 +517,12 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
 
     HK_CUDA(cudaMemsetAsync(hist, 0, (nkeys + 4) * sizeof(uint32_t), st));
     HK_CUDA(cudaMemsetAsync(buckets, 0, nkeys * sizeof(XYZZ<F>), st));
-    k_msm_hist<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window, hist);
+    const uint8_t* skip = bv.skip ? bv.skip + offset : nullptr;
+    k_msm_hist<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window, skip, hist);
     HK_LAUNCH_CHECK(ctx);
     exclusive_scan_u32(ctx, hist, nkeys, d_count);
     k_msm_scatter<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window,
-                                                        item_stride, hist, items, keys);
+                                                        item_stride, skip, hist, items, keys);
     HK_LAUNCH_CHECK(ctx);
     int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2);
     {

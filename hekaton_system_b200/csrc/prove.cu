@@ -144,54 +144,52 @@ __global__ void k_build_commit_scalars(const Fr* __restrict__ w, size_t nw, cons
 }
 
 // ---- finish -----------------------------------------------------------------------------------
-// One block per proof p.  jac = [A x K | B1 x K | L' x K | H x K] (G1);  jacB2 x K (G2);
-// r, s: K Montgomery Fr each.
+// Stage 1 (side stream, overlapped with the L / witness-map / H work): the two scalar multiplications
+// by a fresh point, and the normalisation of A and B2.  One block per proof p.
+//   jacA, jacB1: K each (G1);  jacB2: K (G2);  r, s: K Montgomery Fr.
+//   sab[2p] = s*A, sab[2p+1] = r*B1
 template <class Curve>
 __global__ void __launch_bounds__(96)
-k_prove_finish(const Jacobian<typename Curve::Fq>* jac_all, const Jacobian<typename Curve::Fq2>* jacB2_all,
-               const typename Curve::Fr* r_all, const typename Curve::Fr* s_all, Affine<typename Curve::Fq>* outA_all,
-               Affine<typename Curve::Fq2>* outB_all, Affine<typename Curve::Fq>* outC_all, uint8_t* inf_all, uint32_t K) {
+k_prove_finish_ab(const Jacobian<typename Curve::Fq>* jacA, const Jacobian<typename Curve::Fq>* jacB1,
+                  const Jacobian<typename Curve::Fq2>* jacB2, const typename Curve::Fr* r_all,
+                  const typename Curve::Fr* s_all, XYZZ<typename Curve::Fq>* sab, Affine<typename Curve::Fq>* outA_all,
+                  Affine<typename Curve::Fq2>* outB_all, uint8_t* inf_all) {
     using Fq = typename Curve::Fq;
     using Fq2 = typename Curve::Fq2;
-    __shared__ XYZZ<Fq> sh[2];
     const uint32_t p = blockIdx.x;
-    const Jacobian<Fq> jac[4] = {jac_all[p], jac_all[K + p], jac_all[2 * K + p], jac_all[3 * K + p]};
-    const Jacobian<Fq2>* jacB2 = jacB2_all + p;
-    const typename Curve::Fr* r_m = r_all + p;
-    const typename Curve::Fr* s_m = s_all + p;
-    Affine<Fq>* outA = outA_all + p;
-    Affine<Fq2>* outB = outB_all + p;
-    Affine<Fq>* outC = outC_all + p;
-    uint8_t* inf = inf_all + 3 * p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        if (warp == 0) {
-            auto s = (*s_m).from_mont();
-            sh[0] = scalar_mul<Fq>(jac[0].to_xyzz(), s.r.v);
-        } else if (warp == 1) {
-            auto r = (*r_m).from_mont();
-            sh[1] = scalar_mul<Fq>(jac[1].to_xyzz(), r.r.v);
-        } else {
-            XYZZ<Fq2> b = jacB2[0].to_xyzz();
-            *outB = b.to_affine();
-            inf[1] = b.is_inf() ? 1 : 0;
-        }
+    if (lane != 0) return;
+    if (warp == 0) {
+        XYZZ<Fq> a = jacA[p].to_xyzz();
+        auto s = s_all[p].from_mont();
+        sab[2 * p] = scalar_mul<Fq>(a, s.r.v);
+        outA_all[p] = a.to_affine();
+        inf_all[3 * p + 0] = a.is_inf() ? 1 : 0;
+    } else if (warp == 1) {
+        auto r = r_all[p].from_mont();
+        sab[2 * p + 1] = scalar_mul<Fq>(jacB1[p].to_xyzz(), r.r.v);
+    } else {
+        XYZZ<Fq2> b = jacB2[p].to_xyzz();
+        outB_all[p] = b.to_affine();
+        inf_all[3 * p + 1] = b.is_inf() ? 1 : 0;
     }
-    __syncthreads();
-    if (lane == 0) {
-        if (warp == 0) {
-            XYZZ<Fq> c = sh[0];
-            c.add(sh[1]);
-            c.add(jac[2].to_xyzz());
-            c.add(jac[3].to_xyzz());
-            *outC = c.to_affine();
-            inf[2] = c.is_inf() ? 1 : 0;
-        } else if (warp == 1) {
-            XYZZ<Fq> a = jac[0].to_xyzz();
-            *outA = a.to_affine();
-            inf[0] = a.is_inf() ? 1 : 0;
-        }
-    }
+}
+
+// Stage 2 (main stream, after L' and H): C = s*A + r*B1 + L' + H -> affine.  One thread per proof.
+template <class Curve>
+__global__ void __launch_bounds__(32)
+k_prove_finish_c(const XYZZ<typename Curve::Fq>* sab, const Jacobian<typename Curve::Fq>* jacL,
+                 const Jacobian<typename Curve::Fq>* jacH, Affine<typename Curve::Fq>* outC_all, uint8_t* inf_all,
+                 uint32_t K) {
+    using Fq = typename Curve::Fq;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= K) return;
+    XYZZ<Fq> c = sab[2 * p];
+    c.add(sab[2 * p + 1]);
+    c.add(jacL[p].to_xyzz());
+    c.add(jacH[p].to_xyzz());
+    outC_all[p] = c.to_affine();
+    inf_all[3 * p + 2] = c.is_inf() ? 1 : 0;
 }
 
 // ---- host orchestration -----------------------------------------------------------------------
@@ -392,6 +390,15 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     HK_LAUNCH_CHECK(ctx);
     msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, S, K, false, jac + K);
     msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, S, K, false, jacB2);
+    // s*A, r*B1 and the normalisation of A, B2 need nothing else: run them on the side stream while
+    // the main stream continues with L', the witness map and the H MSM.
+    XYZZ<Fq>* sab = ctx->ws_io[2].as<XYZZ<Fq>>(2 * K);
+    HK_CUDA(cudaEventRecord(ctx->ev_fork, st));
+    HK_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    k_prove_finish_ab<Curve><<<Ku, 96, 0, ctx->side>>>(jac, jac + K, jacB2, r, s, sab, reinterpret_cast<Affine<Fq>*>(d_outA),
+                                                       reinterpret_cast<Affine<Fq2>*>(d_outB), d_inf);
+    HK_LAUNCH_CHECK(ctx);
+    HK_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
     // L'
     const size_t nl = pk.stage_start[ns] - pk.stage_start[ns - 1];
     Fr* Ls = ctx->ws_io[1].as<Fr>(K * (nl + ns));
@@ -407,9 +414,9 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     qap_h_from_evals<Curve>(ctx, log_n, abc, h, K);
     msm_run<Curve, 1>(ctx, msm_view(*pk.h_g), 0, N - 1, reinterpret_cast<const Scalar256*>(h), K, true, jac + 3 * K,
                       /*sc_stride=*/N);
-    k_prove_finish<Curve><<<Ku, 96, 0, st>>>(jac, jacB2, r, s, reinterpret_cast<Affine<Fq>*>(d_outA),
-                                             reinterpret_cast<Affine<Fq2>*>(d_outB),
-                                             reinterpret_cast<Affine<Fq>*>(d_outC), d_inf, Ku);
+    HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    k_prove_finish_c<Curve><<<ceil_div(K, 32), 32, 0, st>>>(sab, jac + 2 * K, jac + 3 * K,
+                                                            reinterpret_cast<Affine<Fq>*>(d_outC), d_inf, Ku);
     HK_LAUNCH_CHECK(ctx);
 }
 template void prove_run<Bls12381>(hk_ctx*, PkDev&, size_t, const uint64_t*, const uint64_t*, const uint64_t*,
