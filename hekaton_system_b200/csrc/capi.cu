@@ -277,6 +277,7 @@ static int32_t ctx_make_side(hk_ctx* ctx) {
     if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) return HK_ERR_CUDA;
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
     if (cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
+    if (cudaEventCreateWithFlags(&ctx->ev_ab, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
     return HK_OK;
 }
 HK_EXPORT int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx** out) {
@@ -332,6 +333,7 @@ HK_EXPORT int32_t hk_ctx_destroy(hk_ctx* ctx) {
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_ab) cudaEventDestroy(ctx->ev_ab);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HK_OK;

@@ -149,6 +149,12 @@ struct ProfRec {
     uint32_t* pinned_units = nullptr;   // filled by an async D2H copy of a device counter
 };
 
+// Scratch of one MSM pipeline; a context has one per lane (main stream, side stream) so two MSMs
+// of the same proof batch can run concurrently.
+struct MsmWs {
+    DevBuf scalars, hist, items, buckets, chunks, wsum, scan, misc;
+};
+
 struct NttDomain;   // ntt.cu
 struct R1csDev;     // qap.cu
 struct PkDev;       // prove.cu
@@ -172,15 +178,17 @@ struct hk_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t side = nullptr;          // helper stream for work that overlaps the main pipeline
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_ab = nullptr, ev_join = nullptr;
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
     std::shared_ptr<hk::SharedState> sh;
 
     // scratch (grow-only; a context is single-threaded by contract)
-    hk::DevBuf ws_scalars, ws_hist, ws_items, ws_buckets, ws_chunks, ws_wsum, ws_out, ws_scan;
-    hk::DevBuf ws_ntt_tmp, ws_qap[4], ws_io[4], ws_z, ws_misc;
+    hk::MsmWs mws[2];                  // lane 0: main stream, lane 1: side stream
+    hk::DevBuf ws_out;
+    hk::DevBuf ws_ntt_tmp, ws_qap[4], ws_io[6], ws_z, ws_misc;
+    cudaStream_t lane_stream(int lane) const { return lane ? side : stream; }
     void* pinned = nullptr;
     size_t pinned_cap = 0;
 
@@ -236,26 +244,28 @@ inline int32_t guarded(hk_ctx* ctx, Fn&& fn) {
     } while (0)
 
 // Bracket one kernel launch with events when profiling is on.
-inline int prof_begin(hk_ctx* ctx, int id) {
+inline int prof_begin(hk_ctx* ctx, int id, cudaStream_t st = nullptr) {
     if (!ctx->prof_on) return -1;
+    if (!st) st = ctx->stream;
     ProfRec r;
     r.id = id;
     HK_CUDA(cudaEventCreate(&r.e0));
     HK_CUDA(cudaEventCreate(&r.e1));
-    HK_CUDA(cudaEventRecord(r.e0, ctx->stream));
+    HK_CUDA(cudaEventRecord(r.e0, st));
     ctx->prof.push_back(r);
     return (int)ctx->prof.size() - 1;
 }
-inline void prof_end(hk_ctx* ctx, int idx, uint64_t static_units, const uint32_t* d_units) {
+inline void prof_end(hk_ctx* ctx, int idx, uint64_t static_units, const uint32_t* d_units, cudaStream_t st = nullptr) {
     if (idx < 0) return;
+    if (!st) st = ctx->stream;
     ProfRec& r = ctx->prof[idx];
-    HK_CUDA(cudaEventRecord(r.e1, ctx->stream));
+    HK_CUDA(cudaEventRecord(r.e1, st));
     r.static_units = static_units;
     if (d_units) {
         if (!ctx->prof_pinned) HK_CUDA(cudaMallocHost((void**)&ctx->prof_pinned, hk_ctx::PROF_SLOTS * sizeof(uint32_t)));
         if (ctx->prof_pinned_used < hk_ctx::PROF_SLOTS) {
             r.pinned_units = ctx->prof_pinned + ctx->prof_pinned_used++;
-            HK_CUDA(cudaMemcpyAsync(r.pinned_units, d_units, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            HK_CUDA(cudaMemcpyAsync(r.pinned_units, d_units, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         }
     }
 }
@@ -266,7 +276,7 @@ inline void prof_end(hk_ctx* ctx, int idx, uint64_t static_units, const uint32_t
 // Jacobian points (device).  sc_stride = 0 means n.
 template <class Curve, int GROUP>
 void msm_run(hk_ctx* ctx, const MsmBases& bases, size_t offset, size_t n, const Scalar256* d_scalars, size_t K,
-             bool scalars_mont, void* d_out_jac, size_t sc_stride = 0);
+             bool scalars_mont, void* d_out_jac, size_t sc_stride = 0, int lane = 0);
 // build the window-shifted table of a base set (no-op if present); density = expected fraction of
 // full-width scalars (1.0 = uniform), steers the window size
 template <class Curve, int GROUP>

@@ -1,6 +1,6 @@
 // Explicit instantiation of the MSM pipeline for Bn254 G2 (one TU per group keeps builds parallel).
 #include "msm_impl.cuh"
 namespace hk {
-template void msm_run<Bn254, 2>(hk_ctx*, const MsmBases&, size_t, size_t, const Scalar256*, size_t, bool, void*, size_t);
+template void msm_run<Bn254, 2>(hk_ctx*, const MsmBases&, size_t, size_t, const Scalar256*, size_t, bool, void*, size_t, int);
 template void bases_precompute<Bn254, 2>(hk_ctx*, BaseSet&, double);
 }

@@ -207,14 +207,14 @@ static __global__ void k_scan_add(uint32_t* data, size_t len, const uint32_t* ti
         if (base + k < len) data[base + k] += add;
 }
 
-inline void exclusive_scan_u32(hk_ctx* ctx, uint32_t* d, size_t len, uint32_t* d_total) {
+inline void exclusive_scan_u32(hk_ctx* ctx, MsmWs& ws, cudaStream_t st, uint32_t* d, size_t len, uint32_t* d_total) {
     size_t ntiles = (len + SCAN_TILE - 1) / SCAN_TILE;
-    uint32_t* sums = ctx->ws_scan.as<uint32_t>(ntiles + 1);
-    k_scan_tiles<<<(unsigned)ntiles, SCAN_TPB, 0, ctx->stream>>>(d, len, sums);
+    uint32_t* sums = ws.scan.as<uint32_t>(ntiles + 1);
+    k_scan_tiles<<<(unsigned)ntiles, SCAN_TPB, 0, st>>>(d, len, sums);
     HK_LAUNCH_CHECK(ctx);
-    k_scan_sums<<<1, 1024, 0, ctx->stream>>>(sums, ntiles, d_total);
+    k_scan_sums<<<1, 1024, 0, st>>>(sums, ntiles, d_total);
     HK_LAUNCH_CHECK(ctx);
-    k_scan_add<<<(unsigned)ntiles, SCAN_TPB, 0, ctx->stream>>>(d, len, sums);
+    k_scan_add<<<(unsigned)ntiles, SCAN_TPB, 0, st>>>(d, len, sums);
     HK_LAUNCH_CHECK(ctx);
 }
 
@@ -435,11 +435,12 @@ void bases_precompute(hk_ctx* ctx, BaseSet& bs, double density) {
 
 template <class Curve, int GROUP>
 void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Scalar256* d_scalars_in, size_t K,
-             bool scalars_mont, void* d_out_jac_v, size_t sc_stride) {
+             bool scalars_mont, void* d_out_jac_v, size_t sc_stride, int lane) {
     using F = typename GroupFieldT<Curve, GROUP>::F;
     using Fr = typename Curve::Fr;
     Jacobian<F>* d_out = reinterpret_cast<Jacobian<F>*>(d_out_jac_v);
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->lane_stream(lane);
+    MsmWs& ws = ctx->mws[lane ? 1 : 0];
     if (K == 0) return;
     if (n == 0) {
         k_set_identity_jac<F><<<ceil_div(K, 128), 128, 0, st>>>(d_out, K);
@@ -471,7 +472,7 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     const Scalar256* d_sc = d_scalars_in;
     if (scalars_mont) {
         // convert the used part of every vector into a dense K x n array
-        Scalar256* conv = ctx->ws_scalars.as<Scalar256>(n * K);
+        Scalar256* conv = ws.scalars.as<Scalar256>(n * K);
         if (sc_stride == n) {
             k_scalars_from_mont<Fr><<<ceil_div(n * K, 256), 256, 0, st>>>(d_scalars_in, conv, n * K);
             HK_LAUNCH_CHECK(ctx);
@@ -484,11 +485,11 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
         d_sc = conv;
         sc_stride = n;
     }
-    uint32_t* hist = ctx->ws_hist.as<uint32_t>(nkeys + 4);
+    uint32_t* hist = ws.hist.as<uint32_t>(nkeys + 4);
     uint32_t* d_count = hist + nkeys;     // total item count lives right after the histogram
-    uint32_t* items = ctx->ws_items.as<uint32_t>(2 * max_items);
+    uint32_t* items = ws.items.as<uint32_t>(2 * max_items);
     uint32_t* keys = items + max_items;
-    XYZZ<F>* buckets = ctx->ws_buckets.as<XYZZ<F>>(nkeys);
+    XYZZ<F>* buckets = ws.buckets.as<XYZZ<F>>(nkeys);
     const uint32_t nthr0 = ceil_div(max_items, S0);
     std::vector<uint32_t> lvl_in;      // entries consumed at fold level l
     {
@@ -502,8 +503,8 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     }
     size_t part_total = 0;
     for (uint32_t v : lvl_in) part_total += v;
-    XYZZ<F>* partial = ctx->ws_chunks.as<XYZZ<F>>(part_total);
-    uint32_t* partial_keys = ctx->ws_misc.as<uint32_t>(part_total);
+    XYZZ<F>* partial = ws.chunks.as<XYZZ<F>>(part_total);
+    uint32_t* partial_keys = ws.misc.as<uint32_t>(part_total);
     // reduction geometry: short serial chunks, then a multi-block tree
     uint32_t G = pl.B >= 32768 ? 8 : (pl.B >= 1024 ? 4 : (pl.B >= 64 ? 2 : 1));
     uint32_t T = pl.B / G;
@@ -513,18 +514,18 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     for (uint32_t m = T; m > 1; m = ceil_div(m, 2 * TS_TPB)) tree.push_back(m);
     size_t tree_total = (size_t)T * nsets;
     for (uint32_t m : tree) tree_total += (size_t)ceil_div(m, 2 * TS_TPB) * nsets;
-    XYZZ<F>* chunk_out = ctx->ws_wsum.as<XYZZ<F>>(tree_total + nsets);
+    XYZZ<F>* chunk_out = ws.wsum.as<XYZZ<F>>(tree_total + nsets);
 
     HK_CUDA(cudaMemsetAsync(hist, 0, (nkeys + 4) * sizeof(uint32_t), st));
     HK_CUDA(cudaMemsetAsync(buckets, 0, nkeys * sizeof(XYZZ<F>), st));
     const uint8_t* skip = bv.skip ? bv.skip + offset : nullptr;
     k_msm_hist<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window, skip, hist);
     HK_LAUNCH_CHECK(ctx);
-    exclusive_scan_u32(ctx, hist, nkeys, d_count);
+    exclusive_scan_u32(ctx, ws, st, hist, nkeys, d_count);
     k_msm_scatter<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window,
                                                         item_stride, skip, hist, items, keys);
     HK_LAUNCH_CHECK(ctx);
-    int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2);
+    int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2, st);
     {
         const dim3 grid(ceil_div(nthr0, 128));
 #define HK_ACC(SS, MB) k_msm_accum<F, SS, MB><<<grid, 128, 0, st>>>(d_bases, items, keys, d_count, buckets, partial, partial_keys, nthr0)
@@ -539,7 +540,7 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
 #undef HK_ACC
     }
     HK_LAUNCH_CHECK(ctx);
-    prof_end(ctx, pi, 0, d_count);
+    prof_end(ctx, pi, 0, d_count, st);
     size_t off = 0;
     for (size_t l = 0; l < lvl_in.size(); l++) {
         uint32_t n_in = lvl_in[l];

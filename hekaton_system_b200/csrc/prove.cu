@@ -96,20 +96,31 @@ k_fixed_base_mul(const XYZZ<F>* __restrict__ tbl, const Scalar256* __restrict__ 
 
 // ---- scalar staging ---------------------------------------------------------------------------
 // S = from_mont([ z[1..m-1], 1, 1, x ])  (m + 2 canonical scalars)
-// blockIdx.y = proof index p in the batch
+// blockIdx.y = proof index p in the batch.  Writes both scalar vectors of the proof:
+//   out_r[p] = from_mont([z[1..], 1, 1, r_p])   (A)      out_s[p] = from_mont([z[1..], 1, 1, s_p])   (B1, B2)
 template <class Fr>
-__global__ void k_build_abc_scalars(const Fr* __restrict__ z_all, size_t m, const Fr* x_all, Scalar256* out_all) {
+__global__ void k_build_abc_scalars(const Fr* __restrict__ z_all, size_t m, const Fr* r_all, const Fr* s_all,
+                                    Scalar256* out_r_all, Scalar256* out_s_all) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= m + 2) return;
     const size_t p = blockIdx.y;
     const Fr* z = z_all + p * m;
-    Scalar256* out = out_all + p * (m + 2);
-    Fr v;
-    if (i < m - 1) v = z[i + 1];
-    else if (i < m + 1) v = Fr::one();
-    else v = x_all[p];
-    v = v.from_mont();
-    for (int k = 0; k < 4; k++) out[i].v[k] = v.r.v[k];
+    Scalar256* out_r = out_r_all + p * (m + 2);
+    Scalar256* out_s = out_s_all + p * (m + 2);
+    if (i < m + 1) {
+        Fr v = (i < m - 1) ? z[i + 1] : Fr::one();
+        v = v.from_mont();
+        for (int k = 0; k < 4; k++) {
+            out_r[i].v[k] = v.r.v[k];
+            out_s[i].v[k] = v.r.v[k];
+        }
+    } else {
+        Fr a = r_all[p].from_mont(), b = s_all[p].from_mont();
+        for (int k = 0; k < 4; k++) {
+            out_r[i].v[k] = a.r.v[k];
+            out_s[i].v[k] = b.r.v[k];
+        }
+    }
 }
 
 // dst[p * stride] = from_mont(x[p])
@@ -381,20 +392,23 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     const unsigned Ku = (unsigned)K;
     Jacobian<Fq>* jac = ctx->ws_out.as<Jacobian<Fq>>(8 * K);        // [A | B1 | L' | H] x K, then B2 x K
     Jacobian<Fq2>* jacB2 = reinterpret_cast<Jacobian<Fq2>*>(jac + 4 * K);
-    // A, B1, B2: shared canonical scalar vectors (one per proof), last entry r then s
-    Scalar256* S = ctx->ws_io[0].as<Scalar256>(K * (m + 2));
-    k_build_abc_scalars<Fr><<<dim3(ceil_div(m + 2, 256), Ku), 256, 0, st>>>(z, m, r, S);
+    // A uses [z.., 1, 1, r]; B1 and B2 use [z.., 1, 1, s]
+    Scalar256* Sr = ctx->ws_io[0].as<Scalar256>(K * (m + 2));
+    Scalar256* Ss = ctx->ws_io[4].as<Scalar256>(K * (m + 2));
+    k_build_abc_scalars<Fr><<<dim3(ceil_div(m + 2, 256), Ku), 256, 0, st>>>(z, m, r, s, Sr, Ss);
     HK_LAUNCH_CHECK(ctx);
-    msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, S, K, false, jac + 0);
-    k_patch_scalar<Fr><<<ceil_div(K, 64), 64, 0, st>>>(s, S + m + 1, m + 2, K);
-    HK_LAUNCH_CHECK(ctx);
-    msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, S, K, false, jac + K);
-    msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, S, K, false, jacB2);
-    // s*A, r*B1 and the normalisation of A, B2 need nothing else: run them on the side stream while
-    // the main stream continues with L', the witness map and the H MSM.
-    XYZZ<Fq>* sab = ctx->ws_io[2].as<XYZZ<Fq>>(2 * K);
+    // side lane: the G2 MSM (latency-heavy reduction stages, 3x slower field) overlaps the G1 work
     HK_CUDA(cudaEventRecord(ctx->ev_fork, st));
     HK_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, Ss, K, false, jacB2, 0, /*lane=*/1);
+    // main lane
+    msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, Sr, K, false, jac + 0);
+    msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, Ss, K, false, jac + K);
+    // s*A, r*B1 and the normalisation of A, B2: side lane, after A and B1 are available; overlaps L',
+    // the witness map and the H MSM on the main lane
+    XYZZ<Fq>* sab = ctx->ws_io[2].as<XYZZ<Fq>>(2 * K);
+    HK_CUDA(cudaEventRecord(ctx->ev_ab, st));
+    HK_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_ab, 0));
     k_prove_finish_ab<Curve><<<Ku, 96, 0, ctx->side>>>(jac, jac + K, jacB2, r, s, sab, reinterpret_cast<Affine<Fq>*>(d_outA),
                                                        reinterpret_cast<Affine<Fq2>*>(d_outB), d_inf);
     HK_LAUNCH_CHECK(ctx);
