@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--shape", default="big-merkle")
     ap.add_argument("--batch", type=int, default=8, help="subcircuits per GPU per step")
     ap.add_argument("--curve", default="bls12_381")
-    ap.add_argument("--streams", type=int, default=2,
+    ap.add_argument("--streams", type=int, default=1,
                     help="concurrent sub-batches per GPU (forked contexts: shared key, own stream + scratch); "
                          "each sub-batch of batch/streams proofs is ONE hk_prove_batch pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -210,14 +210,15 @@ def main():
     chunks = []          # per forked context: contiguous device + host inputs for its sub-batch
     for t in range(nstreams):
         its = items[t * per:(t + 1) * per]
-        hz = np.stack([it["z"] for it in its])
-        hr = np.stack([it["rm"] for it in its])
-        hs = np.stack([it["sm"] for it in its])
-        hk_ = np.stack([it["km"] for it in its])
+        # e2e inputs live in pinned host memory (numpy views of torch pinned tensors)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).pin_memory()
+        pins = [pin(np.stack([it[k] for it in its])) for k in ("z", "rm", "sm", "km")]
+        hz, hr, hs, hk_ = [t_.numpy().view(np.uint64) for t_ in pins]
+        hz = hz.reshape(len(its), -1, 4)
         dz = torch.from_numpy(hz.view(np.int64)).to(dev)
         drsk = torch.from_numpy(np.concatenate([hr.ravel(), hs.ravel(), hk_.ravel()]).view(np.int64)).to(dev)
         out = torch.zeros((per * OUTB + 7) // 8 + 1, dtype=torch.int64, device=dev)
-        chunks.append(dict(hz=hz, hr=hr, hs=hs, hk=hk_, dz=dz, drsk=drsk, out=out))
+        chunks.append(dict(hz=hz, hr=hr, hs=hs, hk=hk_, dz=dz, drsk=drsk, out=out, pins=pins))
     my_subcircuits = shard_range(args.batch * world, world, rank)      # contiguous chunk per rank (node.rs:471-493)
     assert len(my_subcircuits) == args.batch
 
@@ -245,7 +246,7 @@ def main():
 
         def work(t):
             ch = chunks[t]
-            res[t] = ctxs[t].prove_batch(pk.handle, ch["hz"], ch["hr"], ch["hs"], ch["hk"])
+            res[t] = ctxs[t].prove_batch(pk.handle, ch["hz"], ch["hr"], ch["hs"], ch["hk"], pinned=True)
 
         if nstreams == 1:
             work(0)

@@ -11,7 +11,7 @@ import numpy as np
 
 from .curves import get_curve
 
-HK_HOST, HK_DEVICE = 0, 1
+HK_HOST, HK_DEVICE, HK_HOST_PINNED = 0, 1, 2
 SCALAR_BIGINT, SCALAR_MONT = 0, 1
 NTT_FORWARD, NTT_INVERSE = 0, 1
 DOMAIN_PLAIN, DOMAIN_COSET = 0, 1
@@ -339,9 +339,10 @@ class Context:
                                    c.ctypes.data, inf.ctypes.data))
         return a, b, c, inf
 
-    def prove_batch(self, pk, z, r, s, kappas):
+    def prove_batch(self, pk, z, r, s, kappas, pinned=False):
         """K proofs against one key.  Host arrays: z (K, m, 4), r (K, 4), s (K, 4), kappas (K, ns-1, 4)
-        -> (A (K, 2L), B (K, 4L), C (K, 2L), inf (K, 3))."""
+        -> (A (K, 2L), B (K, 4L), C (K, 2L), inf (K, 3)).  pinned=True promises that the input arrays
+        live in page-locked memory (e.g. numpy views of torch pinned tensors): no staging copy."""
         z = np.ascontiguousarray(z, dtype=np.uint64)
         K = z.shape[0]
         r = np.ascontiguousarray(r, dtype=np.uint64).reshape(K, 4)
@@ -352,7 +353,8 @@ class Context:
         c = np.zeros((K, 2 * self.L), dtype=np.uint64)
         inf = np.zeros((K, 3), dtype=np.uint8)
         self._ck(self.lib.hk_prove_batch(self.h, pk, K, z.ctypes.data, r.ctypes.data, s.ctypes.data,
-                                         kappas.ctypes.data if kappas.size else None, HK_HOST, a.ctypes.data,
+                                         kappas.ctypes.data if kappas.size else None,
+                                         HK_HOST_PINNED if pinned else HK_HOST, a.ctypes.data,
                                          b.ctypes.data, c.ctypes.data, inf.ctypes.data))
         return a, b, c, inf
 

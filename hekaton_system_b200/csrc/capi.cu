@@ -275,6 +275,8 @@ float time_ms(hk_ctx* ctx, Fn&& fn) {
 // ==================================================================================================
 static int32_t ctx_make_side(hk_ctx* ctx) {
     if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) return HK_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking) != cudaSuccess) return HK_ERR_CUDA;
+    if (cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
     if (cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
     if (cudaEventCreateWithFlags(&ctx->ev_ab, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
@@ -331,6 +333,11 @@ HK_EXPORT int32_t hk_ctx_destroy(hk_ctx* ctx) {
         cudaStreamSynchronize(ctx->side);
         cudaStreamDestroy(ctx->side);
     }
+    if (ctx->side2) {
+        cudaStreamSynchronize(ctx->side2);
+        cudaStreamDestroy(ctx->side2);
+    }
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_ab) cudaEventDestroy(ctx->ev_ab);
@@ -646,17 +653,35 @@ HK_EXPORT int32_t hk_prove_batch(hk_ctx* ctx, uint64_t pk_h, size_t K, const uin
                      [&] { prove_run<Bn254>(ctx, pk, K, z, r, s, kappas, a_affine, b_affine, c_affine, inf); });
             return;
         }
-        // host staging: [z | r | s | kappas] in one pinned buffer, one H2D copy; one D2H copy back
-        const size_t zb = K * pk.m * 32, rb = K * 32, kb = K * (size_t)nk * 32;
+        // host inputs -> device [z | r | s | kappas]; pageable inputs go through a pinned staging buffer
+        // one proof at a time so the DMA of proof k overlaps the staging copy of proof k+1; pinned
+        // inputs are DMA'd in place.  One D2H copy brings all proofs back.
+        HK_REQUIRE(memspace == HK_HOST || memspace == HK_HOST_PINNED, HK_ERR_INVALID, "bad memspace");
+        const size_t zb1 = pk.m * 32, zb = K * zb1, rb = K * 32, kb = K * (size_t)nk * 32;
         const size_t total = zb + 2 * rb + kb;
         const size_t out_bytes = K * (2 * p1 + p2 + 3);
-        char* pin = (char*)ctx->pinned_buf(total + out_bytes + 64);
-        memcpy(pin, z, zb);
-        memcpy(pin + zb, r, rb);
-        memcpy(pin + zb + rb, s, rb);
-        if (kb) memcpy(pin + zb + 2 * rb, kappas, kb);
         char* dz = (char*)ctx->ws_z.ensure(total + 64);
-        HK_CUDA(cudaMemcpyAsync(dz, pin, total, cudaMemcpyHostToDevice, ctx->stream));
+        char* pin;
+        char* pout;
+        if (memspace == HK_HOST_PINNED) {
+            pin = nullptr;
+            pout = (char*)ctx->pinned_buf(out_bytes + 64);
+            HK_CUDA(cudaMemcpyAsync(dz, z, zb, cudaMemcpyHostToDevice, ctx->stream));
+            HK_CUDA(cudaMemcpyAsync(dz + zb, r, rb, cudaMemcpyHostToDevice, ctx->stream));
+            HK_CUDA(cudaMemcpyAsync(dz + zb + rb, s, rb, cudaMemcpyHostToDevice, ctx->stream));
+            if (kb) HK_CUDA(cudaMemcpyAsync(dz + zb + 2 * rb, kappas, kb, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            pin = (char*)ctx->pinned_buf(total + out_bytes + 64);
+            pout = pin + total;
+            memcpy(pin + zb, r, rb);
+            memcpy(pin + zb + rb, s, rb);
+            if (kb) memcpy(pin + zb + 2 * rb, kappas, kb);
+            HK_CUDA(cudaMemcpyAsync(dz + zb, pin + zb, 2 * rb + kb, cudaMemcpyHostToDevice, ctx->stream));
+            for (size_t k = 0; k < K; k++) {
+                memcpy(pin + k * zb1, (const char*)z + k * zb1, zb1);
+                HK_CUDA(cudaMemcpyAsync(dz + k * zb1, pin + k * zb1, zb1, cudaMemcpyHostToDevice, ctx->stream));
+            }
+        }
         char* d_out = (char*)ctx->ws_io[3].ensure(out_bytes + 64);
         char* dA = d_out;
         char* dB = dA + K * p1;
@@ -668,7 +693,6 @@ HK_EXPORT int32_t hk_prove_batch(hk_ctx* ctx, uint64_t pk_h, size_t K, const uin
         const uint64_t* dk = (const uint64_t*)(dz + zb + 2 * rb);
         by_curve(ctx, [&] { prove_run<Bls12381>(ctx, pk, K, dzz, dr, ds, dk, dA, dB, dC, d_inf); },
                  [&] { prove_run<Bn254>(ctx, pk, K, dzz, dr, ds, dk, dA, dB, dC, d_inf); });
-        char* pout = pin + total;
         HK_CUDA(cudaMemcpyAsync(pout, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         HK_CUDA(cudaStreamSynchronize(ctx->stream));
         memcpy(a_affine, pout, K * p1);

@@ -177,18 +177,24 @@ struct hk_ctx {
     uint32_t curve = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t side = nullptr;          // helper stream for work that overlaps the main pipeline
-    cudaEvent_t ev_fork = nullptr, ev_ab = nullptr, ev_join = nullptr;
+    // helper streams for work that overlaps the main pipeline of a proof batch:
+    //   side  (lane 1): G2 MSM, s*A / r*B1 scalar multiplications, A/B2 normalisation
+    //   side2 (lane 2): witness map (CSR mat-vec + 7 NTTs) and the H MSM
+    cudaStream_t side = nullptr, side2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_ab = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
     std::shared_ptr<hk::SharedState> sh;
 
     // scratch (grow-only; a context is single-threaded by contract)
-    hk::MsmWs mws[2];                  // lane 0: main stream, lane 1: side stream
+    hk::MsmWs mws[3];                  // one MSM scratch per lane
     hk::DevBuf ws_out;
     hk::DevBuf ws_ntt_tmp, ws_qap[4], ws_io[6], ws_z, ws_misc;
-    cudaStream_t lane_stream(int lane) const { return lane ? side : stream; }
+    cudaStream_t lane_stream(int lane) const { return lane == 0 ? stream : (lane == 1 ? side : side2); }
+    // stream used by the NTT / QAP kernels (normally the main stream; prove_run points it at lane 2)
+    cudaStream_t qap_stream = nullptr;
+    cudaStream_t qstream() const { return qap_stream ? qap_stream : stream; }
     void* pinned = nullptr;
     size_t pinned_cap = 0;
 

@@ -440,7 +440,7 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     using Fr = typename Curve::Fr;
     Jacobian<F>* d_out = reinterpret_cast<Jacobian<F>*>(d_out_jac_v);
     cudaStream_t st = ctx->lane_stream(lane);
-    MsmWs& ws = ctx->mws[lane ? 1 : 0];
+    MsmWs& ws = ctx->mws[lane < 0 || lane > 2 ? 0 : lane];
     if (K == 0) return;
     if (n == 0) {
         k_set_identity_jac<F><<<ceil_div(K, 128), 128, 0, st>>>(d_out, K);

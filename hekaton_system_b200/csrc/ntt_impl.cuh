@@ -360,19 +360,19 @@ void ntt_passes(hk_ctx* ctx, const NttDomain& d, bool dit, bool inverse_root, co
         const Fr* pre = first ? pre_scale : nullptr;
         const Fr* post = last ? post_scale : nullptr;
         const Fr* pc = last ? post_const : nullptr;
-        int pidx = prof_begin(ctx, HK_PROF_NTT_PASS);
+        int pidx = prof_begin(ctx, HK_PROF_NTT_PASS, ctx->qstream());
         if (dit)
-            k_ntt_pass<Fr, true><<<grid, NTT_TPB, smem, ctx->stream>>>(cur, to, tw, log_n, ps.s0, ps.k, ps.q, ps.T, pre,
+            k_ntt_pass<Fr, true><<<grid, NTT_TPB, smem, ctx->qstream()>>>(cur, to, tw, log_n, ps.s0, ps.k, ps.q, ps.T, pre,
                                                                        post, pc, flags);
         else
-            k_ntt_pass<Fr, false><<<grid, NTT_TPB, smem, ctx->stream>>>(cur, to, tw, log_n, ps.s0, ps.k, ps.q, ps.T, pre,
+            k_ntt_pass<Fr, false><<<grid, NTT_TPB, smem, ctx->qstream()>>>(cur, to, tw, log_n, ps.s0, ps.k, ps.q, ps.T, pre,
                                                                         post, pc, flags);
         HK_LAUNCH_CHECK(ctx);
-        prof_end(ctx, pidx, (uint64_t)K << log_n, nullptr);
+        prof_end(ctx, pidx, (uint64_t)K << log_n, nullptr, ctx->qstream());
         cur = to;
     }
     if (cur != dst) {
-        HK_CUDA(cudaMemcpyAsync(dst, cur, (K << log_n) * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+        HK_CUDA(cudaMemcpyAsync(dst, cur, (K << log_n) * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->qstream()));
     }
 }
 

@@ -413,7 +413,24 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
                                                        reinterpret_cast<Affine<Fq2>*>(d_outB), d_inf);
     HK_LAUNCH_CHECK(ctx);
     HK_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
-    // L'
+    // lane 2: witness map and the H MSM need only z -- start them right away
+    HK_CUDA(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork, 0));
+    uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N * K);
+    uint64_t* h = ctx->ws_qap[1].as<uint64_t>(4 * N * K);
+    ntt_domain<Curve>(ctx, log_n);                 // build (and synchronise) the tables before switching streams
+    ctx->qap_stream = ctx->side2;
+    try {
+        r1cs_evals<Curve>(ctx, *pk.r1cs, d_z_v, abc, K);
+        qap_h_from_evals<Curve>(ctx, log_n, abc, h, K);
+    } catch (...) {
+        ctx->qap_stream = nullptr;
+        throw;
+    }
+    ctx->qap_stream = nullptr;
+    msm_run<Curve, 1>(ctx, msm_view(*pk.h_g), 0, N - 1, reinterpret_cast<const Scalar256*>(h), K, true, jac + 3 * K,
+                      /*sc_stride=*/N, /*lane=*/2);
+    HK_CUDA(cudaEventRecord(ctx->ev_join2, ctx->side2));
+    // main lane: L'
     const size_t nl = pk.stage_start[ns] - pk.stage_start[ns - 1];
     Fr* Ls = ctx->ws_io[1].as<Fr>(K * (nl + ns));
     k_build_l_scalars<Fr><<<dim3(ceil_div(nl + ns, 256), Ku), 256, 0, st>>>(
@@ -421,14 +438,8 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     HK_LAUNCH_CHECK(ctx);
     msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[ns - 1]), 0, nl + ns, reinterpret_cast<const Scalar256*>(Ls), K, true,
                       jac + 2 * K);
-    // h and H
-    uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N * K);
-    uint64_t* h = ctx->ws_qap[1].as<uint64_t>(4 * N * K);
-    r1cs_evals<Curve>(ctx, *pk.r1cs, d_z_v, abc, K);
-    qap_h_from_evals<Curve>(ctx, log_n, abc, h, K);
-    msm_run<Curve, 1>(ctx, msm_view(*pk.h_g), 0, N - 1, reinterpret_cast<const Scalar256*>(h), K, true, jac + 3 * K,
-                      /*sc_stride=*/N);
     HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
     k_prove_finish_c<Curve><<<ceil_div(K, 32), 32, 0, st>>>(sab, jac + 2 * K, jac + 3 * K,
                                                             reinterpret_cast<Affine<Fq>*>(d_outC), d_inf, Ku);
     HK_LAUNCH_CHECK(ctx);

@@ -69,7 +69,7 @@ void qap_h_from_evals(hk_ctx* ctx, uint32_t log_n, uint64_t* d_abc_v, uint64_t* 
     // 3K x coset fft from bit-reversed coefficients; scale g^rev(p)/N folded into the load
     ntt_passes<Curve>(ctx, *dom, true, false, abc, abc, tmp, 3 * K, false, false,
                       reinterpret_cast<const Fr*>(dom->coset_br), nullptr, nullptr);
-    k_qap_pointwise<Fr><<<dim3(ceil_div(N, 256), (unsigned)K), 256, 0, ctx->stream>>>(
+    k_qap_pointwise<Fr><<<dim3(ceil_div(N, 256), (unsigned)K), 256, 0, ctx->qstream()>>>(
         abc, (uint32_t)N, reinterpret_cast<const Fr*>(dom->zh_inv), ab);
     HK_LAUNCH_CHECK(ctx);
     // K x coset ifft: DIF(w^-1), last pass scales by g^-j/N (indexed by destination j) and un-permutes
@@ -83,7 +83,7 @@ void r1cs_evals(hk_ctx* ctx, const R1csDev& m, const uint64_t* d_z, uint64_t* d_
     using Fr = typename Curve::Fr;
     const uint32_t N = 1u << m.log_n;
     if (K == 0) return;
-    k_r1cs_evals<Fr><<<dim3(ceil_div(N, 128), (unsigned)K), 128, 0, ctx->stream>>>(
+    k_r1cs_evals<Fr><<<dim3(ceil_div(N, 128), (unsigned)K), 128, 0, ctx->qstream()>>>(
         m.ptr[0], m.col[0], reinterpret_cast<const Fr*>(m.val[0]), m.ptr[1], m.col[1],
         reinterpret_cast<const Fr*>(m.val[1]), m.ptr[2], m.col[2], reinterpret_cast<const Fr*>(m.val[2]),
         reinterpret_cast<const Fr*>(d_z), (uint32_t)m.n, (uint32_t)m.l, N, reinterpret_cast<Fr*>(d_abc), m.l + m.nw);

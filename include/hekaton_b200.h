@@ -34,7 +34,9 @@
  *     representation of ark-ec `short_weierstrass::Projective`.  Any representative of the
  *     group element may be returned; equality with the reference is after into_affine().
  *   - `memspace`: HK_HOST = pointers are host memory (copies are part of the call),
- *     HK_DEVICE = pointers are device memory on the context's GPU (no copies).
+ *     HK_DEVICE = pointers are device memory on the context's GPU (no copies),
+ *     HK_HOST_PINNED (hk_prove_batch / hk_prove inputs only) = host memory that is already
+ *     page-locked: inputs are DMA'd straight from the caller's buffers, no staging copy.
  *   - A context is bound to one GPU and one CUDA stream and is not thread-safe; use one
  *     context per host thread (the reference runs several proofs concurrently on separate
  *     threads, mpi-snark/src/bin/node.rs:773-793).  Calls with HK_HOST outputs
@@ -53,7 +55,7 @@ extern "C" {
 typedef struct hk_ctx hk_ctx;
 
 enum { HK_CURVE_BLS12_381 = 0, HK_CURVE_BN254 = 1 };
-enum { HK_HOST = 0, HK_DEVICE = 1 };
+enum { HK_HOST = 0, HK_DEVICE = 1, HK_HOST_PINNED = 2 };
 enum { HK_SCALAR_BIGINT = 0, HK_SCALAR_MONT = 1 };
 enum { HK_NTT_FORWARD = 0, HK_NTT_INVERSE = 1 };
 enum { HK_DOMAIN_PLAIN = 0, HK_DOMAIN_COSET_GENERATOR = 1 };
