@@ -5,6 +5,7 @@
     python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference path
 
 Metric (BASELINE.json): subcircuit proofs/s.  A "step" proves one batch of synthetic subcircuits
+(stage-0 commitment + stage-1 proof each, as the reference's workers do: mpi-snark/src/worker.rs:48-85)
 of the big-merkle shape (BASELINE config 3: 64 subcircuits x 4 SHA2 iters, 8 portals ->
 n = 200 000 constraints, domain N = 2^18, BLS12-381), `--batch` subcircuits per GPU per step;
 subcircuits are independent, so ranks shard them with no data-path collective and only gather
@@ -182,14 +183,17 @@ def main():
         threads = os.cpu_count() or 1
         it = items[0]
         for _ in range(min(args.warmup, 1)):
+            cp.commit(0, it["z"], it["km"], threads=threads)
             cp.prove(it["z"], it["rm"], it["sm"], it["km"], threads=threads)
         t0 = time.time()
         for i in range(args.steps):
             it = items[i % len(items)]
-            cp.prove(it["z"], it["rm"], it["sm"], it["km"], threads=threads)
+            cp.commit(0, it["z"], it["km"], threads=threads)                    # stage 0 (committer.rs:55-98)
+            cp.prove(it["z"], it["rm"], it["sm"], it["km"], threads=threads)    # stage 1 (committer.rs:100-122)
         dt = time.time() - t0
         v = args.steps / dt
-        sample = f"{args.steps} proof(s) of the same workload, one per step (bounded sample of the {args.batch}-proof step)"
+        sample = (f"{args.steps} subcircuit(s) (commit + prove) of the same workload, one per step "
+                  f"(bounded sample of the {args.batch}-subcircuit step)")
         print(json.dumps({
             "impl": "reference", "metric": "subcircuit proofs/s", "value": v, "unit": "proofs/s", "n_gpus": 0,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
@@ -207,6 +211,7 @@ def main():
     assert args.batch % nstreams == 0, "--batch must be a multiple of --streams"
     per = args.batch // nstreams
     OUTB = 2 * P1 + P2 + 3
+    COMB = P1 + 1
     chunks = []          # per forked context: contiguous device + host inputs for its sub-batch
     for t in range(nstreams):
         its = items[t * per:(t + 1) * per]
@@ -217,7 +222,7 @@ def main():
         hz = hz.reshape(len(its), -1, 4)
         dz = torch.from_numpy(hz.view(np.int64)).to(dev)
         drsk = torch.from_numpy(np.concatenate([hr.ravel(), hs.ravel(), hk_.ravel()]).view(np.int64)).to(dev)
-        out = torch.zeros((per * OUTB + 7) // 8 + 1, dtype=torch.int64, device=dev)
+        out = torch.zeros((per * (OUTB + COMB) + 63) // 8 + 4, dtype=torch.int64, device=dev)
         chunks.append(dict(hz=hz, hr=hr, hs=hs, hk=hk_, dz=dz, drsk=drsk, out=out, pins=pins))
     my_subcircuits = shard_range(args.batch * world, world, rank)      # contiguous chunk per rank (node.rs:471-493)
     assert len(my_subcircuits) == args.batch
@@ -229,6 +234,9 @@ def main():
         for t, ch in enumerate(chunks):
             q = ch["drsk"].data_ptr()
             p = ch["out"].data_ptr()
+            pc = p + ((per * OUTB + 15) // 16) * 16
+            # stage 0: commitments (committer.rs:55-98); stage 1: proofs (committer.rs:100-122)
+            ctxs[t].commit_batch_device(pk.handle, 0, per, ch["dz"].data_ptr(), wl.m, q + 64 * per, pc, pc + per * P1)
             ctxs[t].prove_batch_device(pk.handle, per, ch["dz"].data_ptr(), q, q + 32 * per, q + 64 * per,
                                        p, p + per * P1, p + per * (P1 + P2), p + per * (2 * P1 + P2))
         for ws in wstreams[1:]:
@@ -246,7 +254,8 @@ def main():
 
         def work(t):
             ch = chunks[t]
-            res[t] = ctxs[t].prove_batch(pk.handle, ch["hz"], ch["hr"], ch["hs"], ch["hk"], pinned=True)
+            com = ctxs[t].commit_batch(pk.handle, 0, ch["hz"], ch["hk"])
+            res[t] = (com, ctxs[t].prove_batch(pk.handle, ch["hz"], ch["hr"], ch["hs"], ch["hk"], pinned=True))
 
         if nstreams == 1:
             work(0)
@@ -347,11 +356,12 @@ def main():
                 cp = cpu_prover_for(ctx, wl, pk)
                 threads = os.cpu_count() or 1
                 t0 = time.time()
+                cp.commit(0, it0["z"], it0["km"], threads=threads)
                 ca, cb, cc = cp.prove(it0["z"], it0["rm"], it0["sm"], it0["km"], threads=threads)
                 dt = time.time() - t0
                 same = bool(np.array_equal(ca, a) and np.array_equal(cb, b) and np.array_equal(cc, c))
                 cpu = {"value": 1.0 / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
-                       "sample": "1 proof of the same workload (same key, same assignment as step 0)",
+                       "sample": "1 subcircuit (commit + prove) of the same workload (same key, same assignment as step 0)",
                        "seconds": dt, "bit_exact_with_gpu": same}
             except Exception as e:       # the baseline is a report, never a dependency of the product path
                 cpu = {"value": None, "unit": "proofs/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
@@ -361,7 +371,7 @@ def main():
             "vs_baseline": None, "dtype": "u32x2 (Montgomery Fq/Fr on 32x32+64 IMAD.WIDE lanes)", "data": "synthetic",
             "config": config, "clocks": clocks,
             "e2e": {"value": e2e_v, "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": args.batch * (wl.m * 32 + 96), "d2h_bytes_per_step": args.batch * OUTB},
+                    "h2d_bytes_per_step": args.batch * (wl.m * 32 + 96), "d2h_bytes_per_step": args.batch * (OUTB + COMB)},
             "gpu_launches": launches, "roofline": roof, "roofline_ntt": roof_ntt, "cpu_baseline": cpu,
             "verified_vs_trapdoor": verified,
         }

@@ -84,6 +84,7 @@ def load_library(path=None):
         "hk_pk_create": [vp, C.POINTER(PkDesc), C.POINTER(u64)],
         "hk_pk_free": [vp, u64],
         "hk_commit": [vp, u64, u32, u64p, u64p, u32, vp, u8p],
+        "hk_commit_batch": [vp, u64, u32, sz, u64p, sz, u64p, u32, vp, u8p],
         "hk_prove": [vp, u64, u64p, u64p, u64p, u64p, u32, vp, vp, vp, u8p],
         "hk_prove_batch": [vp, u64, sz, u64p, u64p, u64p, u64p, u32, vp, vp, vp, u8p],
         "hk_field_op": [vp, u32, u32, u64p, u64p, u64p, sz],
@@ -323,6 +324,20 @@ class Context:
         self._ck(self.lib.hk_commit(self.h, pk, stage, z.ctypes.data, kappa.ctypes.data, HK_HOST, out.ctypes.data,
                                     inf.ctypes.data))
         return out, bool(inf[0])
+
+    def commit_batch(self, pk, stage, z, kappa):
+        """K commitments: host arrays z (K, m, 4), kappa (K, 4) -> (points (K, 2L), inf (K,))."""
+        z = np.ascontiguousarray(z, dtype=np.uint64)
+        K = z.shape[0]
+        kappa = np.ascontiguousarray(kappa, dtype=np.uint64).reshape(K, 4)
+        out = np.zeros((K, 2 * self.L), dtype=np.uint64)
+        inf = np.zeros(K, dtype=np.uint8)
+        self._ck(self.lib.hk_commit_batch(self.h, pk, stage, K, z.ctypes.data, z.shape[1], kappa.ctypes.data, HK_HOST,
+                                          out.ctypes.data, inf.ctypes.data))
+        return out, inf
+
+    def commit_batch_device(self, pk, stage, K, z, z_stride, kappa, out, inf):
+        self._ck(self.lib.hk_commit_batch(self.h, pk, stage, K, z, z_stride, kappa, HK_DEVICE, out, inf))
 
     def prove(self, pk, z, r, s, kappas):
         """Host buffers in, host buffers out: (A (2L), B (4L), C (2L), inf[3])."""

@@ -31,6 +31,12 @@ const void* to_device(hk_ctx* ctx, DevBuf& buf, const void* p, size_t bytes, uin
     return d;
 }
 
+// device pointers handed to kernels that use 128-bit vector accesses
+void require_aligned16(const void* p, const char* what) {
+    HK_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, HK_ERR_INVALID,
+               std::string(what) + ": device pointers must be 16-byte aligned");
+}
+
 uint64_t new_handle(hk_ctx* ctx) {
     std::lock_guard<std::mutex> lk(ctx->sh->mu);
     return ctx->sh->next_handle++;
@@ -143,6 +149,10 @@ void msm_entry(hk_ctx* ctx, int group, uint64_t bases, size_t base_offset, const
                 HK_CUDA(cudaMemcpyAsync(d + k * len, (const Scalar256*)scalars + k * n, len * 32, cudaMemcpyHostToDevice,
                                         ctx->stream));
         d_sc = d;
+    }
+    if (memspace == HK_DEVICE) {
+        require_aligned16(scalars, "hk_msm scalars");
+        require_aligned16(out, "hk_msm out");
     }
     void* d_out = (memspace == HK_DEVICE) ? out : ctx->ws_out.ensure(jb * K + 64);
     const MsmBases bv = msm_view(bs);
@@ -613,27 +623,52 @@ HK_EXPORT int32_t hk_pk_free(hk_ctx* ctx, uint64_t pk_handle) {
     });
 }
 
-HK_EXPORT int32_t hk_commit(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, const uint64_t* z, const uint64_t* kappa,
-                            uint32_t memspace, void* com_affine, uint8_t* com_inf) {
+HK_EXPORT int32_t hk_commit_batch(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, size_t K, const uint64_t* z,
+                                  size_t z_stride, const uint64_t* kappa, uint32_t memspace, void* com_affine,
+                                  uint8_t* com_inf) {
     return guarded(ctx, [&] {
         auto pksp = find_pk(ctx, pk_h);
         HK_REQUIRE(z && kappa && com_affine, HK_ERR_INVALID, "NULL argument");
         PkDev& pk = *pksp;
         HK_REQUIRE(stage < pk.num_stages, HK_ERR_INVALID, "commit: no such stage");
+        if (K == 0) return;
         const size_t need = pk.r1cs->l + pk.stage_start[stage + 1];
-        const uint64_t* dz = (const uint64_t*)to_device(ctx, ctx->ws_z, z, need * 32, memspace);
-        const uint64_t* dk = (const uint64_t*)to_device(ctx, ctx->ws_io[2], kappa, 32, memspace);
+        HK_REQUIRE(z_stride >= need || K == 1, HK_ERR_INVALID, "commit: z_stride shorter than the committed prefix");
         const size_t pb = point_bytes(ctx, 1);
-        char* d_out = memspace == HK_DEVICE ? (char*)com_affine : (char*)ctx->ws_io[3].ensure(pb + 64);
-        uint8_t* d_inf = memspace == HK_DEVICE ? com_inf : (uint8_t*)(d_out + pb);
-        by_curve(ctx, [&] { commit_run<Bls12381>(ctx, pk, stage, dz, dk, d_out, d_inf); },
-                 [&] { commit_run<Bn254>(ctx, pk, stage, dz, dk, d_out, d_inf); });
-        if (memspace != HK_DEVICE) {
-            HK_CUDA(cudaMemcpyAsync(com_affine, d_out, pb, cudaMemcpyDeviceToHost, ctx->stream));
-            if (com_inf) HK_CUDA(cudaMemcpyAsync(com_inf, d_inf, 1, cudaMemcpyDeviceToHost, ctx->stream));
-            HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (memspace == HK_DEVICE) {
+            HK_REQUIRE(com_inf, HK_ERR_INVALID, "com_inf is NULL");
+            require_aligned16(z, "hk_commit z");
+            require_aligned16(kappa, "hk_commit kappa");
+            require_aligned16(com_affine, "hk_commit com_affine");
+            by_curve(ctx, [&] { commit_run<Bls12381>(ctx, pk, stage, K, z, z_stride, kappa, com_affine, com_inf); },
+                     [&] { commit_run<Bn254>(ctx, pk, stage, K, z, z_stride, kappa, com_affine, com_inf); });
+            return;
         }
+        // host: only the committed prefix of every assignment is copied (stride `need` on the device)
+        char* dz = (char*)ctx->ws_z.ensure(K * need * 32 + K * 32 + 64);
+        for (size_t k = 0; k < K; k++)
+            HK_CUDA(cudaMemcpyAsync(dz + k * need * 32, (const char*)z + k * z_stride * 32, need * 32, cudaMemcpyHostToDevice,
+                                    ctx->stream));
+        char* dk = dz + K * need * 32;
+        HK_CUDA(cudaMemcpyAsync(dk, kappa, K * 32, cudaMemcpyHostToDevice, ctx->stream));
+        char* d_out = (char*)ctx->ws_io[3].ensure(K * (pb + 1) + 64);
+        uint8_t* d_inf = (uint8_t*)(d_out + K * pb);
+        by_curve(ctx,
+                 [&] { commit_run<Bls12381>(ctx, pk, stage, K, (const uint64_t*)dz, need, (const uint64_t*)dk, d_out, d_inf); },
+                 [&] { commit_run<Bn254>(ctx, pk, stage, K, (const uint64_t*)dz, need, (const uint64_t*)dk, d_out, d_inf); });
+        HK_CUDA(cudaMemcpyAsync(com_affine, d_out, K * pb, cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<uint8_t> tmp(K);
+        HK_CUDA(cudaMemcpyAsync(tmp.data(), d_inf, K, cudaMemcpyDeviceToHost, ctx->stream));
+        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (com_inf) memcpy(com_inf, tmp.data(), K);
     });
+}
+
+HK_EXPORT int32_t hk_commit(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, const uint64_t* z, const uint64_t* kappa,
+                            uint32_t memspace, void* com_affine, uint8_t* com_inf) {
+    uint8_t scratch = 0;
+    if (memspace == HK_DEVICE && !com_inf) return HK_ERR_INVALID;
+    return hk_commit_batch(ctx, pk_h, stage, 1, z, 0, kappa, memspace, com_affine, com_inf ? com_inf : &scratch);
 }
 
 HK_EXPORT int32_t hk_prove_batch(hk_ctx* ctx, uint64_t pk_h, size_t K, const uint64_t* z, const uint64_t* r,
@@ -649,6 +684,13 @@ HK_EXPORT int32_t hk_prove_batch(hk_ctx* ctx, uint64_t pk_h, size_t K, const uin
         const uint32_t nk = pk.num_stages - 1;
         if (memspace == HK_DEVICE) {
             HK_REQUIRE(inf, HK_ERR_INVALID, "inf is NULL");
+            require_aligned16(z, "hk_prove z");
+            require_aligned16(r, "hk_prove r");
+            require_aligned16(s, "hk_prove s");
+            if (kappas) require_aligned16(kappas, "hk_prove kappas");
+            require_aligned16(a_affine, "hk_prove a");
+            require_aligned16(b_affine, "hk_prove b");
+            require_aligned16(c_affine, "hk_prove c");
             by_curve(ctx, [&] { prove_run<Bls12381>(ctx, pk, K, z, r, s, kappas, a_affine, b_affine, c_affine, inf); },
                      [&] { prove_run<Bn254>(ctx, pk, K, z, r, s, kappas, a_affine, b_affine, c_affine, inf); });
             return;

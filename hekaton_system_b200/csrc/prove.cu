@@ -146,14 +146,6 @@ __global__ void k_build_l_scalars(const Fr* __restrict__ z_all, size_t m, size_t
     else out[i] = kappas[p * nk + (i - nl - 1)].neg();
 }
 
-// commit scalars (Montgomery): [ w_stage (nw), kappa ]
-template <class Fr>
-__global__ void k_build_commit_scalars(const Fr* __restrict__ w, size_t nw, const Fr* kappa, Fr* out) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i > nw) return;
-    out[i] = (i < nw) ? w[i] : *kappa;
-}
-
 // ---- finish -----------------------------------------------------------------------------------
 // Stage 1 (side stream, overlapped with the L / witness-map / H work): the two scalar multiplications
 // by a fresh point, and the normalisation of A and B2.  One block per proof p.
@@ -355,24 +347,39 @@ std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d) {
 template std::shared_ptr<PkDev> pk_create<Bls12381>(hk_ctx*, const hk_pk_desc&);
 template std::shared_ptr<PkDev> pk_create<Bn254>(hk_ctx*, const hk_pk_desc&);
 
+// commit scalars (Montgomery), per proof p (blockIdx.y): [ w_stage (nw), kappa_p ]
+template <class Fr>
+__global__ void k_build_commit_scalars(const Fr* __restrict__ z_all, size_t z_stride, size_t w_off, size_t nw,
+                                       const Fr* kappa, Fr* out_all) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i > nw) return;
+    const size_t p = blockIdx.y;
+    const Fr* w = z_all + p * z_stride + w_off;
+    out_all[p * (nw + 1) + i] = (i < nw) ? w[i] : kappa[p];
+}
+
+// K commitments of one stage in one pipeline.  z: K assignments, `z_stride` elements apart, each at
+// least l + stage_start[stage+1] long; kappa: K; out: K affine points + K infinity flags.
 template <class Curve>
-void commit_run(hk_ctx* ctx, PkDev& pk, uint32_t stage, const uint64_t* d_z, const uint64_t* d_kappa,
-                void* d_out_affine, uint8_t* d_inf) {
+void commit_run(hk_ctx* ctx, PkDev& pk, uint32_t stage, size_t K, const uint64_t* d_z, size_t z_stride,
+                const uint64_t* d_kappa, void* d_out_affine, uint8_t* d_inf) {
     using Fr = typename Curve::Fr;
     using Fq = typename Curve::Fq;
     HK_REQUIRE(stage < pk.num_stages, HK_ERR_INVALID, "commit: no such stage (\"no more values left in committing key\")");
+    if (K == 0) return;
     const size_t l = pk.r1cs->l;
     const size_t nw = pk.stage_start[stage + 1] - pk.stage_start[stage];
-    const Fr* w = reinterpret_cast<const Fr*>(d_z) + l + pk.stage_start[stage];
-    Fr* sc = ctx->ws_io[0].as<Fr>(nw + 1);
-    k_build_commit_scalars<Fr><<<ceil_div(nw + 1, 256), 256, 0, ctx->stream>>>(w, nw, reinterpret_cast<const Fr*>(d_kappa), sc);
+    Fr* sc = ctx->ws_io[0].as<Fr>(K * (nw + 1));
+    k_build_commit_scalars<Fr><<<dim3(ceil_div(nw + 1, 256), (unsigned)K), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const Fr*>(d_z), z_stride, l + pk.stage_start[stage], nw, reinterpret_cast<const Fr*>(d_kappa), sc);
     HK_LAUNCH_CHECK(ctx);
-    Jacobian<Fq>* jac = ctx->ws_out.as<Jacobian<Fq>>(8);
-    msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[stage]), 0, nw + 1, reinterpret_cast<const Scalar256*>(sc), 1, true, jac);
-    jac_to_affine<Curve, 1>(ctx, jac, d_out_affine, d_inf, 1);
+    Jacobian<Fq>* jac = ctx->ws_out.as<Jacobian<Fq>>(8 * K);
+    msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[stage]), 0, nw + 1, reinterpret_cast<const Scalar256*>(sc), K, true, jac);
+    jac_to_affine<Curve, 1>(ctx, jac, d_out_affine, d_inf, K);
 }
-template void commit_run<Bls12381>(hk_ctx*, PkDev&, uint32_t, const uint64_t*, const uint64_t*, void*, uint8_t*);
-template void commit_run<Bn254>(hk_ctx*, PkDev&, uint32_t, const uint64_t*, const uint64_t*, void*, uint8_t*);
+template void commit_run<Bls12381>(hk_ctx*, PkDev&, uint32_t, size_t, const uint64_t*, size_t, const uint64_t*, void*,
+                                   uint8_t*);
+template void commit_run<Bn254>(hk_ctx*, PkDev&, uint32_t, size_t, const uint64_t*, size_t, const uint64_t*, void*, uint8_t*);
 
 template <class Curve>
 void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const uint64_t* d_r, const uint64_t* d_s,

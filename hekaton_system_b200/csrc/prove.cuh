@@ -27,8 +27,8 @@ void fixed_base_mul(hk_ctx* ctx, const void* d_gen_affine, const Scalar256* d_sc
 template <class Curve>
 std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d);
 template <class Curve>
-void commit_run(hk_ctx* ctx, PkDev& pk, uint32_t stage, const uint64_t* d_z, const uint64_t* d_kappa,
-                void* d_out_affine, uint8_t* d_inf);
+void commit_run(hk_ctx* ctx, PkDev& pk, uint32_t stage, size_t K, const uint64_t* d_z, size_t z_stride,
+                const uint64_t* d_kappa, void* d_out_affine, uint8_t* d_inf);
 // K proofs against the same key in one pipeline: z K x m, r/s K, kappas K x (ns-1); outputs K each
 template <class Curve>
 void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z, const uint64_t* d_r, const uint64_t* d_s,

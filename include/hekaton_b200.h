@@ -34,7 +34,8 @@
  *     representation of ark-ec `short_weierstrass::Projective`.  Any representative of the
  *     group element may be returned; equality with the reference is after into_affine().
  *   - `memspace`: HK_HOST = pointers are host memory (copies are part of the call),
- *     HK_DEVICE = pointers are device memory on the context's GPU (no copies),
+ *     HK_DEVICE = pointers are device memory on the context's GPU (no copies; field-element and
+ *     point pointers must be 16-byte aligned -- HK_ERR_INVALID otherwise),
  *     HK_HOST_PINNED (hk_prove_batch / hk_prove inputs only) = host memory that is already
  *     page-locked: inputs are DMA'd straight from the caller's buffers, no staging copy.
  *   - A context is bound to one GPU and one CUDA stream and is not thread-safe; use one
@@ -188,6 +189,10 @@ int32_t hk_pk_free(hk_ctx* ctx, uint64_t pk_handle);
  * kappa: Montgomery Fr.  out: G1 affine (x||y Montgomery), inf flag. */
 int32_t hk_commit(hk_ctx* ctx, uint64_t pk, uint32_t stage, const uint64_t* z, const uint64_t* kappa,
                   uint32_t memspace, void* com_affine, uint8_t* com_inf);
+/* K commitments of one stage against the same key in one pipeline; assignment k starts at
+ * z + k * z_stride * 4 (z_stride in field elements, >= l + stage_start[stage+1]). */
+int32_t hk_commit_batch(hk_ctx* ctx, uint64_t pk, uint32_t stage, size_t K, const uint64_t* z, size_t z_stride,
+                        const uint64_t* kappa, uint32_t memspace, void* com_affine, uint8_t* com_inf);
 /* prover.rs:53-156 + committer.rs:106-114.  z: full assignment (Montgomery Fr),
  * r, s: Montgomery Fr, kappas: num_stages-1 Montgomery Fr.
  * out: A (G1 affine), B (G2 affine), C (G1 affine), each x||y Montgomery; inf[3]. */

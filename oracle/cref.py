@@ -30,7 +30,7 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB):
-            subprocess.check_call(["make", "-C", os.path.join(HERE, "c")])
+            subprocess.check_call(["make", "-C", os.path.join(HERE, "c")], stdout=subprocess.DEVNULL)
         _lib = C.CDLL(LIB)
         _lib.orc_max_threads.restype = C.c_int
     return _lib
@@ -126,10 +126,25 @@ class CpuProver:
             self.keep.append(arr)
             setattr(pk, nm, arr.ctypes.data)
         cks = [u64(c) for c in ck]
+        self._ck = cks
+        self._deltas = u64(deltas_g)
+        self._stage_start = [int(x) for x in stage_start]
         self.keep += cks
         self.ck_arr = (C.c_void_p * len(cks))(*[c.ctypes.data for c in cks])
         pk.ck = C.cast(self.ck_arr, C.POINTER(C.c_void_p))
         self.pk = pk
+
+    def commit(self, stage, z, kappa, threads=1):
+        """committer.rs:85-91 on the CPU: MSM(ck_stage, w_stage) + kappa * last_delta_g, evaluated as one
+        MSM over [ck.., delta_last] with scalars [w.., kappa] (same group element)."""
+        L = self.L
+        ss = self._stage_start
+        l = self.pk.l
+        ck = self._ck[stage]
+        w = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1, 4)[l + ss[stage]:l + ss[stage + 1]]
+        bases = np.concatenate([ck.reshape(-1, 2 * L), self._deltas.reshape(-1, 2 * L)[-1:]])
+        sc = np.concatenate([w, np.ascontiguousarray(kappa, dtype=np.uint64).reshape(1, 4)])
+        return msm(self.curve_id, 1, bases, None, sc, repr_=1, threads=threads)
 
     def prove(self, z, r, s, kappas, threads=1):
         L = self.L

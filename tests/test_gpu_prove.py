@@ -69,10 +69,13 @@ def test_prove_batch_matches_single(ctx):
         zs.append(codec.to_mont(c2.full_assignment(), cv.r, 4))
         rs.append(rng.randrange(cv.r)); ss.append(rng.randrange(cv.r)); ks.append(rng.randrange(cv.r))
     fr = lambda v: codec.to_mont(v, cv.r, 4)
+    com, cinf = ctx.commit_batch(pk.handle, 0, np.stack(zs), fr(ks))
+    assert not cinf.any()
     a, b, c, inf = ctx.prove_batch(pk.handle, np.stack(zs), fr(rs), fr(ss), fr(ks).reshape(K, 1, 4))
     assert not inf.any()
     for k in range(K):
         exp = og.trapdoor_expected(opk, asg[k], td, rs[k], ss[k], [ks[k]])
+        assert codec.g1_affine_from_limbs(com[k], cv)[0] == exp["D"][0]
         assert codec.g1_affine_from_limbs(a[k], cv)[0] == exp["A"]
         assert codec.g2_affine_from_limbs(b[k], cv)[0] == exp["B"]
         assert codec.g1_affine_from_limbs(c[k], cv)[0] == exp["C"]
