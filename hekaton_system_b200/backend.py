@@ -21,7 +21,8 @@ FOP_MUL, FOP_ADD, FOP_SUB, FOP_INV, FOP_TO_MONT, FOP_FROM_MONT = range(6)
 ERRORS = {0: "HK_OK", -1: "HK_ERR_INVALID", -2: "HK_ERR_CUDA", -3: "HK_ERR_NOMEM", -4: "HK_ERR_LENGTH",
           -5: "HK_ERR_HANDLE", -6: "HK_ERR_UNSUPPORTED", -7: "HK_ERR_NO_DEVICE"}
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhekaton_b200.so")
+LIB_PATH = os.environ.get("HK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                    "libhekaton_b200.so")   # HK_LIB: A/B builds of the same ABI
 
 
 class HkError(RuntimeError):

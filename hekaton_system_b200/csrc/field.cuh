@@ -29,6 +29,16 @@ HK_DEFINE_FIELD_TAG(bls12_381_fr)
 HK_DEFINE_FIELD_TAG(bn254_fq)
 HK_DEFINE_FIELD_TAG(bn254_fr)
 
+// Instruction-cache option: with -DHK_MUL_CALL the Montgomery product is a real function (by-value
+// arguments stay in registers: CALL.REL + ~26 MOVs), so a kernel holds ONE copy of the ~7 KB body
+// instead of one per call site (a mixed addition inlines ten of them).
+template <class Tag>
+__device__ __noinline__ typename Tag::raw_t fp_mul_call(typename Tag::raw_t a, typename Tag::raw_t b) {
+    typename Tag::raw_t r;
+    Tag::mul(r, a, b);
+    return r;
+}
+
 template <class Tag>
 struct Fp {
     using raw_t = typename Tag::raw_t;
@@ -62,10 +72,18 @@ struct Fp {
     }
     __device__ __forceinline__ bool operator!=(const Fp& b) const { return !(*this == b); }
 
+#ifdef HK_MUL_CALL
+    __device__ __forceinline__ Fp operator*(const Fp& b) const { Fp o; o.r = fp_mul_call<Tag>(r, b.r); return o; }
+#else
     __device__ __forceinline__ Fp operator*(const Fp& b) const { Fp o; Tag::mul(o.r, r, b.r); return o; }
+#endif
     __device__ __forceinline__ Fp operator+(const Fp& b) const { Fp o; Tag::add(o.r, r, b.r); return o; }
     __device__ __forceinline__ Fp operator-(const Fp& b) const { Fp o; Tag::sub(o.r, r, b.r); return o; }
+#ifdef HK_MUL_CALL
+    __device__ __forceinline__ Fp sqr() const { Fp o; o.r = fp_mul_call<Tag>(r, r); return o; }
+#else
     __device__ __forceinline__ Fp sqr() const { Fp o; Tag::mul(o.r, r, r); return o; }
+#endif
     __device__ __forceinline__ Fp dbl() const { Fp o; Tag::add(o.r, r, r); return o; }
     __device__ __forceinline__ Fp neg() const { Fp z = zero(); Fp o; Tag::sub(o.r, z.r, r); return o; }
 

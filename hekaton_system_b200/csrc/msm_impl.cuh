@@ -462,10 +462,11 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     const size_t max_items = n * K * (size_t)pl.W;
     HK_REQUIRE(nkeys < (size_t(1) << 31), HK_ERR_UNSUPPORTED, "msm: too many buckets for one batch");
     HK_REQUIRE(max_items < (size_t(1) << 32), HK_ERR_UNSUPPORTED, "msm: batch * n * windows must be < 2^32");
-    // level-0 segment length / occupancy variant (HK_ACCUM_S in {32,64,128}, HK_ACCUM_MINB in {2,3,4};
+    // level-0 segment length / occupancy variant (HK_ACCUM_S in {32,64,128}, HK_ACCUM_MINB in {2,3,4}, default 4:
+    // with the call-based multiply 4 CTAs/SM at 128 registers beat 2 at 206 -- profiles/r01c;
     // G2 always uses MINB = 1)
     static const int env_s = getenv("HK_ACCUM_S") ? atoi(getenv("HK_ACCUM_S")) : 32;
-    static const int env_minb = getenv("HK_ACCUM_MINB") ? atoi(getenv("HK_ACCUM_MINB")) : 2;
+    static const int env_minb = getenv("HK_ACCUM_MINB") ? atoi(getenv("HK_ACCUM_MINB")) : 4;
     const int S0 = (env_s == 64 || env_s == 128) ? env_s : 32;
     constexpr int S1 = 16;   // fold segment length
 

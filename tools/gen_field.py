@@ -326,7 +326,10 @@ class FieldGen:
         names = ["a", "b"][:nin]
         inc = ", ".join(f'"l"({nm}.v[{i}])' for nm in names for i in range(n2))
         args = ", ".join(f"const {self.name}_t& {nm}" for nm in names)
-        return (f"__device__ __forceinline__ void {self.name}_{fname}({self.name}_t& r, {args}) {{\n"
+        # HK_MUL_CALL=1 emits the big multiplies as real functions (one copy of the ~7 KB body per kernel
+        # instead of one per call site) -- an instruction-cache experiment, see DESIGN.md
+        attr = "__noinline__" if (fname == "mul" and os.environ.get("HK_MUL_CALL") == "1") else "__forceinline__"
+        return (f"__device__ {attr} void {self.name}_{fname}({self.name}_t& r, {args}) {{\n"
                 f"    asm(\n{body}\n        : {outc}\n        : {inc});\n}}\n")
 
 
