@@ -119,7 +119,7 @@ __device__ __forceinline__ void sm_store(uint4* lo, uint4* hi, uint32_t e, const
 
 // One pass.  grid = (N >> T, K).  in/out may alias when no permutation flag is set.
 template <class Fr, bool DIT>
-__global__ void __launch_bounds__(NTT_TPB)
+__global__ void __launch_bounds__(NTT_TPB, 2)      // <= 64 registers: 2-3 CTAs (32-48 warps) per SM -- profiles/r01c
 k_ntt_pass(const Fr* in_all, Fr* out_all, const Fr* __restrict__ tw, uint32_t log_n,
            uint32_t s0, uint32_t k, uint32_t q, uint32_t T, const Fr* __restrict__ pre_scale,
            const Fr* __restrict__ post_scale, const Fr* __restrict__ post_const, uint32_t flags) {
@@ -330,10 +330,13 @@ void ntt_passes(hk_ctx* ctx, const NttDomain& d, bool dit, bool inverse_root, co
     auto plan = ntt_plan(log_n);
     const Fr* tw = reinterpret_cast<const Fr*>(inverse_root ? d.tw_inv : d.tw_fwd);
     const size_t np = plan.size();
-    if (dit)
+    if (dit) {
         HK_CUDA(cudaFuncSetAttribute(k_ntt_pass<Fr, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    else
+        HK_CUDA(cudaFuncSetAttribute(k_ntt_pass<Fr, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    } else {
         HK_CUDA(cudaFuncSetAttribute(k_ntt_pass<Fr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        HK_CUDA(cudaFuncSetAttribute(k_ntt_pass<Fr, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
     // Buffer routing.  A pass carrying a permutation must run out of place; any other pass may
     // run in place.  `src` is only overwritten when src == dst or the caller allows it.
     const Fr* cur = src;
