@@ -45,6 +45,7 @@ def parse():
                     help="concurrent sub-batches per GPU (forked contexts: shared key, own stream + scratch); "
                          "each sub-batch of batch/streams proofs is ONE hk_prove_batch pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the standalone MSM / NTT measurements")
     return ap.parse_args()
 
 
@@ -122,6 +123,59 @@ def cpu_prover_for(ctx, wl, pk):
     return cref.CpuProver(ctx.curve.cid, wl.n, wl.l, wl.nw, wl.csr, wl.stage_start, dl(h["a_g"], 1), dl(h["b_g"], 1),
                           dl(h["b_h"], 2), dl(h["h_g"], 1), [dl(c, 1) for c in h["ck"]], dl(h["deltas_g"], 1),
                           pk.points["alpha_g"], pk.points["beta_g"], pk.points["beta_h"], pk.points["last_delta_h"])
+
+
+def measure_extras(ctx, stream, imad_peak, hbm_gbs):
+    """Standalone G1 MSM at 2^20 (uniform 255-bit scalars, resident bases with window table) and Fr NTT
+    at 2^20 / 2^24, device-resident, CUDA events on the context stream, best of 5 after warm-up."""
+    import torch
+    from hekaton_system_b200 import codec
+    cv = ctx.curve
+    L = cv.fq_limbs
+    rng = np.random.default_rng(7)
+    out = {}
+
+    def best_ms(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return min(ts)
+
+    n = 1 << 20
+    ks = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    ks[:, 3] >>= 2
+    h = ctx.bases_from_scalars(1, codec.g1_affine_to_limbs([cv.g1], cv)[0], ks)
+    ctx.bases_precompute(h, 1.0)
+    sc = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] >>= 2
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    d_out = torch.zeros(64, dtype=torch.int64, device="cuda")
+    ms = best_ms(lambda: ctx.msm(1, h, d_sc.data_ptr(), n=n, out=d_out.data_ptr()))
+    n32 = 2 * L
+    W, c = 16, 16                           # planner's choice at this size (msm_plan, table mode)
+    macs = n * W * 10 * (2 * n32 * n32 + n32)
+    out["msm_g1_2p20"] = {"ms": ms, "Mpts_per_s": n / ms / 1e3, "window_bits": c, "windows": W,
+                          "algorithmic_wide_macs": macs, "frac_of_imad_peak": macs / (ms * 1e-3) / imad_peak,
+                          "note": "whole MSM (sort + accumulate + reduce), scalars and bases resident in HBM"}
+    ctx.bases_free(h)
+    del d_sc
+    for lg in (20, 24):
+        N = 1 << lg
+        a = rng.integers(0, 1 << 60, size=(N, 4), dtype=np.uint64)
+        d = torch.from_numpy(a.view(np.int64)).cuda()
+        ms = best_ms(lambda: ctx.ntt(d.data_ptr(), lg))
+        gbs = 64 * N / (ms * 1e-3) / 1e9
+        out[f"ntt_fwd_2p{lg}"] = {"ms": ms, "GBps_algorithmic": gbs, "frac_of_hbm_peak": gbs / hbm_gbs,
+                                  "Gbutterflies_per_s": N / 2 * lg / ms / 1e6}
+        del d
+    return out
 
 
 def main():
@@ -321,6 +375,12 @@ def main():
     ms_e2e = timed(step_host, args.steps)
     clocks = sampler.stop() if sampler else None
 
+    # secondary headline figures (BASELINE.json metric: "G1 MSM Mpts/s at 2^20"; north_star: MSM / NTT
+    # throughput with roofline fractions), measured per GPU on rank 0 after the timed regions
+    extras = None
+    if rank == 0 and not args.no_extras:
+        extras = measure_extras(ctx, stream, imad_peak, peaks()[0])
+
     proofs = args.batch * world * args.steps
     value = proofs / (ms_dev * 1e-3)
     e2e_v = proofs / (ms_e2e * 1e-3)
@@ -372,7 +432,7 @@ def main():
             "config": config, "clocks": clocks,
             "e2e": {"value": e2e_v, "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": args.batch * (wl.m * 32 + 96), "d2h_bytes_per_step": args.batch * (OUTB + COMB)},
-            "gpu_launches": launches, "roofline": roof, "roofline_ntt": roof_ntt, "cpu_baseline": cpu,
+            "gpu_launches": launches, "roofline": roof, "roofline_ntt": roof_ntt, "cpu_baseline": cpu, "extras": extras,
             "verified_vs_trapdoor": verified,
         }
         print(json.dumps(line))
