@@ -79,3 +79,37 @@ def test_prove_batch_matches_single(ctx):
         assert codec.g1_affine_from_limbs(a[k], cv)[0] == exp["A"]
         assert codec.g2_affine_from_limbs(b[k], cv)[0] == exp["B"]
         assert codec.g1_affine_from_limbs(c[k], cv)[0] == exp["C"]
+
+
+def test_circom_reference_fixture_end_to_end(ctx):
+    """The circuit of the reference's own `.r1cs` fixture (circom-compat/src/lib.rs:548-600), loaded by
+    hekaton_system_b200.circom, a satisfying witness, a trapdoor key -> device witness map, commit and
+    prove equal the oracle and the trapdoor known answer."""
+    import os
+    from hekaton_system_b200 import circom, codec
+    from oracle import poly
+    cv = ctx.curve
+    if cv.name != "bn254":
+        pytest.skip("circom files are BN254-only, like the reference's reader")
+    r = cv.r
+    data = bytes.fromhex(open(os.path.join(os.path.dirname(__file__), "golden", "circom_sample.r1cs.hex")).read().strip())
+    f = circom.R1CSFile.read(data)
+    # (3w5+8w6)(2w0+20w2+12w3) = 5w0+7w2 ; (4w1+8w4+3w5)(44w3+6w6) = 0 ; (4w6)(6w0+11w2+5w3) = 600w6
+    wires = [1, 12345, 1, 0, 67890, 2 * pow(11, -1, r) % r, 0]
+    staged = f.to_staged(wires, num_stage0=1)
+    r1 = poly.R1CS(staged.l, len(staged.witness), *staged.rows)
+    z = staged.full_assignment()
+    assert r1.is_satisfied(z, r)
+    circ = og.StagedCircuit(r1, staged.stage_ranges, staged.instance, staged.witness)
+    h_ref = poly.witness_map(cv.name, r1, z)
+    rh = ctx.r1cs_upload(staged.num_constraints, staged.l, len(staged.witness), staged.csr())
+    h = ctx.witness_map(rh, codec.to_mont(z, r, 4), n_out=len(h_ref))
+    assert codec.from_mont(h, r) == h_ref
+    td = og.sample_trapdoor(cv.name, 2, 99)
+    opk = og.generate_parameters(cv.name, circ, td)
+    pk = host.ProvingKey.from_key(ctx, opk, circ)
+    cb = host.CommitmentBuilder(staged, pk)
+    com, kap = cb.commit(kappa=4242)
+    proof = cb.prove([com], [kap], r=777, s=888)
+    exp = og.trapdoor_expected(opk, circ, td, 777, 888, [4242])
+    assert (com, proof.a, proof.b, proof.c) == (exp["D"][0], exp["A"], exp["B"], exp["C"])
