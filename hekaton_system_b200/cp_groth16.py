@@ -25,12 +25,99 @@ from . import codec
 from .backend import SCALAR_MONT
 
 
+# ---- ark-serialize 0.4 encodings (CanonicalSerialize) -----------------------------------------------------
+# Restated from the published crate (third-party, un-vendored): field elements are canonical
+# little-endian bytes (8 per limb); a short-Weierstrass affine point is x (|| y when uncompressed) with two
+# flag bits OR-ed into the most significant byte written last: 0x80 = "y is the larger of {y, -y}", 0x40 =
+# point at infinity (then x = y = 0); Fq2 = c0 || c1 and compares c1 first; Vec<T> = u64 LE length + items.
+# PINNING: unpinned (the reference has no serialized fixture and cannot be built here).
+def _y_is_negative_fq(y, p):
+    return y > (p - y) % p
+
+
+def _y_is_negative_fq2(y, p):
+    ny = ((p - y[0]) % p, (p - y[1]) % p)
+    return (y[1], y[0]) > (ny[1], ny[0])
+
+
+def serialize_g1(P, curve, compress=False):
+    nb = 8 * curve.fq_limbs
+    if P is None:
+        b = bytearray(nb if compress else 2 * nb)
+        b[-1] |= 0x40
+        return bytes(b)
+    x, y = P
+    b = bytearray(x.to_bytes(nb, "little") + (b"" if compress else y.to_bytes(nb, "little")))
+    if _y_is_negative_fq(y, curve.p):
+        b[-1] |= 0x80
+    return bytes(b)
+
+
+def serialize_g2(P, curve, compress=False):
+    nb = 8 * curve.fq_limbs
+    if P is None:
+        b = bytearray(2 * nb if compress else 4 * nb)
+        b[-1] |= 0x40
+        return bytes(b)
+    (x0, x1), (y0, y1) = P
+    b = bytearray(x0.to_bytes(nb, "little") + x1.to_bytes(nb, "little") +
+                  (b"" if compress else y0.to_bytes(nb, "little") + y1.to_bytes(nb, "little")))
+    if _y_is_negative_fq2((y0, y1), curve.p):
+        b[-1] |= 0x80
+    return bytes(b)
+
+
+def _deser_fq(buf, nb, last=False):
+    b = bytearray(buf[:nb])
+    flags = 0
+    if last:
+        flags = b[-1] & 0xC0
+        b[-1] &= 0x3F
+    return int.from_bytes(b, "little"), flags
+
+
+def deserialize_g1_uncompressed(buf, curve):
+    nb = 8 * curve.fq_limbs
+    x, _ = _deser_fq(buf, nb)
+    y, flags = _deser_fq(buf[nb:], nb, last=True)
+    return None if flags & 0x40 else (x, y)
+
+
+def deserialize_g2_uncompressed(buf, curve):
+    nb = 8 * curve.fq_limbs
+    x0, _ = _deser_fq(buf, nb)
+    x1, _ = _deser_fq(buf[nb:], nb)
+    y0, _ = _deser_fq(buf[2 * nb:], nb)
+    y1, flags = _deser_fq(buf[3 * nb:], nb, last=True)
+    return None if flags & 0x40 else ((x0, x1), (y0, y1))
+
+
 @dataclass
 class Proof:
     a: tuple
     b: tuple
     c: tuple
     ds: list = field(default_factory=list)
+
+    def serialize(self, curve, compress=False):
+        """`#[derive(CanonicalSerialize)] struct Proof { a, b, c, ds }` (data_structures.rs:7-16)."""
+        out = serialize_g1(self.a, curve, compress) + serialize_g2(self.b, curve, compress)
+        out += serialize_g1(self.c, curve, compress)
+        out += len(self.ds).to_bytes(8, "little")
+        for d in self.ds:
+            out += serialize_g1(d, curve, compress)
+        return out
+
+    @classmethod
+    def deserialize_uncompressed(cls, buf, curve):
+        nb = 8 * curve.fq_limbs
+        a = deserialize_g1_uncompressed(buf, curve)
+        b = deserialize_g2_uncompressed(buf[2 * nb:], curve)
+        c = deserialize_g1_uncompressed(buf[6 * nb:], curve)
+        n = int.from_bytes(buf[8 * nb:8 * nb + 8], "little")
+        off = 8 * nb + 8
+        ds = [deserialize_g1_uncompressed(buf[off + 2 * nb * i:], curve) for i in range(n)]
+        return cls(a, b, c, ds)
 
 
 class StagedAssignment:
