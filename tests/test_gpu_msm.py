@@ -182,3 +182,33 @@ def test_forked_contexts_share_resources(ctx):
     for f in forks:
         f.close()
     ctx.bases_free(h)
+
+
+@pytest.mark.parametrize("group,log_n", [(1, 20), (2, 18)])
+def test_msm_full_size_exact(ctx, group, log_n):
+    """BASELINE.json's headline size (G1 MSM at 2^20; G2 at 2^18), window-table mode, checked EXACTLY:
+    bases are k_i * G generated on the device, so the expected result is (sum k_i s_i mod r) * G."""
+    cv = ctx.curve
+    if cv.name != "bls12_381":
+        pytest.skip("full-size run on the primary curve")
+    G = groups(cv.name)[group - 1]
+    n = 1 << log_n
+    rng = np.random.default_rng(log_n)
+    ks = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    ks[:, 3] >>= 2
+    enc = codec.g1_affine_to_limbs if group == 1 else codec.g2_affine_to_limbs
+    h = ctx.bases_from_scalars(group, enc([G.gen], cv)[0], ks)
+    ctx.bases_precompute(h, 1.0)
+    sc = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] >>= 2
+    sc[::7] = 0
+    sc[1::7] = 0
+    sc[1::7, 0] = 1                      # some zeros and ones, like witness vectors
+    jac = ctx.msm(group, h, sc)
+    aff, inf = ctx.into_affine(group, jac)
+    dec = codec.g1_affine_from_limbs if group == 1 else codec.g2_affine_from_limbs
+    ki = codec.limbs_to_ints(ks)
+    si = codec.limbs_to_ints(sc)
+    e = sum(a * b for a, b in zip(ki, si)) % cv.r
+    assert dec(aff, cv, inf)[0] == G.mul(G.gen, e)
+    ctx.bases_free(h)
