@@ -190,6 +190,11 @@ void into_affine_entry(hk_ctx* ctx, int group, const void* jac, size_t n, void* 
 
 // ---- element-wise field ops (test hook) ---------------------------------------------------------
 template <class F>
+__device__ __forceinline__ auto inv_gcd_or_fermat(const F& x, int) -> decltype(x.inverse_gcd()) { return x.inverse_gcd(); }
+template <class F>
+__device__ __forceinline__ F inv_gcd_or_fermat(const F& x, long) { return x.inverse(); }   // Fq2: no GCD variant
+
+template <class F>
 __global__ void k_field_op(const F* a, const F* b, F* out, size_t n, uint32_t op) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -201,6 +206,7 @@ __global__ void k_field_op(const F* a, const F* b, F* out, size_t n, uint32_t op
         case HK_FOP_SUB: r = x - b[i]; break;
         case HK_FOP_INV: r = x.inverse(); break;
         case HK_FOP_TO_MONT: r = x.to_mont(); break;
+        case HK_FOP_INV_GCD: r = inv_gcd_or_fermat<F>(x, 0); break;
         default: r = x.from_mont(); break;
     }
     out[i] = r;
@@ -757,7 +763,7 @@ HK_EXPORT int32_t hk_field_op(hk_ctx* ctx, uint32_t field, uint32_t op, const ui
                               uint64_t* out, size_t n) {
     return guarded(ctx, [&] {
         HK_REQUIRE(a && out, HK_ERR_INVALID, "NULL argument");
-        HK_REQUIRE(op <= HK_FOP_FROM_MONT, HK_ERR_INVALID, "bad op");
+        HK_REQUIRE(op <= HK_FOP_INV_GCD, HK_ERR_INVALID, "bad op");
         HK_REQUIRE(b || op >= HK_FOP_INV, HK_ERR_INVALID, "b is NULL");
         if (n == 0) return;
         bool bls = ctx->curve == HK_CURVE_BLS12_381;

@@ -120,6 +120,94 @@ struct Fp {
         return acc;
     }
 
+    // Inverse by the binary extended Euclidean algorithm: shifts, adds and compares only, so it runs on
+    // the ALU pipe and leaves the multiplier pipe to other warps (Fermat costs ~570 multiplies).  Used by
+    // the batch-affine MSM rounds, one inversion per thread batch.  Montgomery in, Montgomery out; 0 -> 0.
+    __device__ __noinline__ Fp inverse_gcd() const {
+        if (is_zero()) return zero();
+        uint64_t u[N64], v[N64], x1[N64], x2[N64], p[N64];
+#pragma unroll
+        for (int i = 0; i < N64; i++) {
+            u[i] = r.v[i];
+            p[i] = Tag::mod(i);
+            v[i] = p[i];
+            x1[i] = 0;
+            x2[i] = 0;
+        }
+        x1[0] = 1;
+        auto is_one = [](const uint64_t* a) {
+            uint64_t o = a[0] ^ 1;
+#pragma unroll
+            for (int i = 1; i < N64; i++) o |= a[i];
+            return o == 0;
+        };
+        auto shr1 = [](uint64_t* a, uint64_t top) {       // a = (top:a) >> 1
+#pragma unroll
+            for (int i = 0; i < N64 - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 63);
+            a[N64 - 1] = (a[N64 - 1] >> 1) | (top << 63);
+        };
+        auto add_to = [](uint64_t* a, const uint64_t* b) -> uint64_t {      // a += b, returns carry
+            unsigned __int128 c = 0;
+#pragma unroll
+            for (int i = 0; i < N64; i++) {
+                c += (unsigned __int128)a[i] + b[i];
+                a[i] = (uint64_t)c;
+                c >>= 64;
+            }
+            return (uint64_t)c;
+        };
+        auto sub_from = [](uint64_t* a, const uint64_t* b) -> uint64_t {    // a -= b, returns borrow
+            uint64_t bw = 0;
+#pragma unroll
+            for (int i = 0; i < N64; i++) {
+                unsigned __int128 d = (unsigned __int128)a[i] - b[i] - bw;
+                a[i] = (uint64_t)d;
+                bw = (uint64_t)(d >> 64) & 1;
+            }
+            return bw;
+        };
+        auto geq = [](const uint64_t* a, const uint64_t* b) {
+#pragma unroll
+            for (int i = N64 - 1; i >= 0; i--) {
+                if (a[i] != b[i]) return a[i] > b[i];
+            }
+            return true;
+        };
+        auto halve_mod = [&](uint64_t* x) {               // x = x / 2 mod p
+            uint64_t top = 0;
+            if (x[0] & 1) top = add_to(x, p);
+            shr1(x, top);
+        };
+        auto sub_mod = [&](uint64_t* x, const uint64_t* y) {   // x = x - y mod p
+            if (sub_from(x, y)) add_to(x, p);
+        };
+        // invariants: x1 * a = u, x2 * a = v (mod p); gcd(a, p) = 1 so the loop ends with u == 1 or v == 1
+        for (int it = 0; it < 4 * BITS + 8; it++) {
+            if (is_one(u) || is_one(v)) break;
+            if (!(u[0] & 1)) {
+                shr1(u, 0);
+                halve_mod(x1);
+            } else if (!(v[0] & 1)) {
+                shr1(v, 0);
+                halve_mod(x2);
+            } else if (geq(u, v)) {
+                sub_from(u, v);
+                sub_mod(x1, x2);
+            } else {
+                sub_from(v, u);
+                sub_mod(x2, x1);
+            }
+        }
+        Fp raw;                                           // raw = (a R)^-1 = a^-1 R^-1 as an integer mod p
+        const uint64_t* res = is_one(u) ? x1 : x2;
+#pragma unroll
+        for (int i = 0; i < N64; i++) raw.r.v[i] = res[i];
+        Fp rr;
+#pragma unroll
+        for (int i = 0; i < N64; i++) rr.r.v[i] = Tag::r2(i);
+        return (raw * rr) * rr;                           // a^-1 R^-1 * R^2 * R^-1 * R^2 * R^-1 = a^-1 R
+    }
+
     // small-integer constant in Montgomery form (k * R mod p) by repeated addition
     __device__ __forceinline__ static Fp from_small(unsigned k) {
         Fp acc = zero(), o = one();

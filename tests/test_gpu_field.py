@@ -43,6 +43,9 @@ def test_prime_field_ops(ctx, field):
     am = [x * R % mod for x in a[:200]]
     got = codec.limbs_to_ints(ctx.field_op(field, B.FOP_INV, codec.ints_to_limbs(am, L)))
     assert got == [(pow(x, -1, mod) * R % mod) if x % mod else 0 for x in a[:200]]
+    # binary-GCD inverse (ALU-pipe variant used by the batch-affine rounds): same values
+    got = codec.limbs_to_ints(ctx.field_op(field, B.FOP_INV_GCD, codec.ints_to_limbs(am, L)))
+    assert got == [(pow(x, -1, mod) * R % mod) if x % mod else 0 for x in a[:200]]
 
 
 def test_fq2_ops(ctx):
