@@ -46,6 +46,13 @@ def parse():
                          "each sub-batch of batch/streams proofs is ONE hk_prove_batch pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the standalone MSM / NTT measurements")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE config 2 instead of the proof bench: checked G1/G2 MSM + Fr NTT sweep 2^16..2^24 "
+                         "(tools/sweep.py; one JSON line per point)")
+    ap.add_argument("--sweep-args", default="", help="extra arguments for tools/sweep.py")
+    ap.add_argument("--timeline", default=None,
+                    help="diagnostic: write the kernel timeline (name, stream, start, duration) of ONE warm step to "
+                         "this file (torch.profiler / CUPTI) and exit; prints no bench line")
     return ap.parse_args()
 
 
@@ -191,6 +198,14 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    if args.sweep:
+        if rank != 0:
+            return 0
+        import __graft_entry__ as entry
+        entry.build()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sweep
+        return sweep.main(["--curve", args.curve] + args.sweep_args.split())
     torch.cuda.set_device(local)
     if world > 1 and args.impl == "ours":
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -212,6 +227,10 @@ def main():
     nstreams = max(1, min(args.streams, args.batch))
     wstreams = [stream] + [torch.cuda.Stream(device=local) for _ in range(nstreams - 1)]
     ctxs = [ctx] + [ctx.fork(stream=s_.cuda_stream) for s_ in wstreams[1:]]
+    # stage-0 commitments of a sub-batch run on their own forked context (own stream + scratch), so the
+    # small latency-bound commitment MSM overlaps the head of the stage-1 proof pipeline
+    cstreams = [torch.cuda.Stream(device=local) for _ in range(nstreams)]
+    cctxs = [ctx.fork(stream=s_.cuda_stream) for s_ in cstreams]
     cv = ctx.curve
     t0 = time.time()
     wl = workload.make_workload(cv, args.shape, seed=1, num_assignments=2)
@@ -283,17 +302,17 @@ def main():
 
     def step_device():
         # fan out: every worker stream starts after the main stream, the main stream joins them all
-        for ws in wstreams[1:]:
+        for ws in wstreams[1:] + cstreams:
             ws.wait_stream(stream)
         for t, ch in enumerate(chunks):
             q = ch["drsk"].data_ptr()
             p = ch["out"].data_ptr()
             pc = p + ((per * OUTB + 15) // 16) * 16
             # stage 0: commitments (committer.rs:55-98); stage 1: proofs (committer.rs:100-122)
-            ctxs[t].commit_batch_device(pk.handle, 0, per, ch["dz"].data_ptr(), wl.m, q + 64 * per, pc, pc + per * P1)
+            cctxs[t].commit_batch_device(pk.handle, 0, per, ch["dz"].data_ptr(), wl.m, q + 64 * per, pc, pc + per * P1)
             ctxs[t].prove_batch_device(pk.handle, per, ch["dz"].data_ptr(), q, q + 32 * per, q + 64 * per,
                                        p, p + per * P1, p + per * (P1 + P2), p + per * (2 * P1 + P2))
-        for ws in wstreams[1:]:
+        for ws in wstreams[1:] + cstreams:
             stream.wait_stream(ws)
         if world > 1:
             # the path's one exchange step: proof records to every rank (aggregation input)
@@ -304,19 +323,18 @@ def main():
     def step_host():
         # one host thread per context, like the reference's per-proof OS threads (node.rs:745-795);
         # each call copies its assignments H2D, proves the sub-batch, and copies the proofs back
-        res = [None] * nstreams
+        res = [None] * (2 * nstreams)
 
-        def work(t):
-            ch = chunks[t]
-            com = ctxs[t].commit_batch(pk.handle, 0, ch["hz"], ch["hk"])
-            res[t] = (com, ctxs[t].prove_batch(pk.handle, ch["hz"], ch["hr"], ch["hs"], ch["hk"], pinned=True))
+        def work(j):
+            t, ch = j // 2, chunks[j // 2]
+            if j % 2 == 0:
+                res[j] = cctxs[t].commit_batch(pk.handle, 0, ch["hz"], ch["hk"])
+            else:
+                res[j] = ctxs[t].prove_batch(pk.handle, ch["hz"], ch["hr"], ch["hs"], ch["hk"], pinned=True)
 
-        if nstreams == 1:
-            work(0)
-        else:
-            ths = [threading.Thread(target=work, args=(t,)) for t in range(nstreams)]
-            [t.start() for t in ths]
-            [t.join() for t in ths]
+        ths = [threading.Thread(target=work, args=(j,)) for j in range(2 * nstreams)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
         return res
 
     def timed(fn, steps):
@@ -355,18 +373,36 @@ def main():
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
+    if args.timeline:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as tp:
+            step_device()
+            torch.cuda.synchronize()
+        tmp = args.timeline + ".chrome.json"
+        tp.export_chrome_trace(tmp)
+        tr = json.load(open(tmp))
+        os.unlink(tmp)
+        evs = [e for e in tr["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+        t0_ = min(e["ts"] for e in evs)
+        sids = {s_: i for i, s_ in enumerate(sorted({e["args"].get("stream") for e in evs}))}
+        with open(args.timeline, "w") as f:
+            f.write("# start_us dur_us stream kernel\n")
+            for e in sorted(evs, key=lambda e: e["ts"]):
+                f.write(f"{e['ts'] - t0_:10.1f} {e['dur']:9.1f} s{sids[e['args'].get('stream')]} {e['name'][:100]}\n")
+        ctx.close()
+        return 0
     sampler = ClockSampler(local) if rank == 0 else None
-    for c_ in ctxs:
+    for c_ in ctxs + cctxs:
         c_.profile_reset()
         c_.profile(True)
-    l0 = sum(c_.launches for c_ in ctxs)
+    l0 = sum(c_.launches for c_ in ctxs + cctxs)
     ms_dev = timed(step_device, args.steps)
-    launches = sum(c_.launches for c_ in ctxs) - l0
+    launches = sum(c_.launches for c_ in ctxs + cctxs) - l0
     prof = {}
     for k in (0, 1, 2):
-        rs = [c_.profile_read(k) for c_ in ctxs]
+        rs = [c_.profile_read(k) for c_ in ctxs + cctxs]
         prof[k] = tuple(sum(x[j] for x in rs) for j in range(3))
-    for c_ in ctxs:
+    for c_ in ctxs + cctxs:
         c_.profile(False)
         c_.profile_reset()
     # end-to-end through the host-buffer C-ABI call
@@ -436,7 +472,7 @@ def main():
             "verified_vs_trapdoor": verified,
         }
         print(json.dumps(line))
-    for c_ in ctxs[1:]:
+    for c_ in ctxs[1:] + cctxs:
         c_.close()
     ctx.close()
     if world > 1:

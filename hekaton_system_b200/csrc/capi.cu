@@ -190,11 +190,6 @@ void into_affine_entry(hk_ctx* ctx, int group, const void* jac, size_t n, void* 
 
 // ---- element-wise field ops (test hook) ---------------------------------------------------------
 template <class F>
-__device__ __forceinline__ auto inv_gcd_or_fermat(const F& x, int) -> decltype(x.inverse_gcd()) { return x.inverse_gcd(); }
-template <class F>
-__device__ __forceinline__ F inv_gcd_or_fermat(const F& x, long) { return x.inverse(); }   // Fq2: no GCD variant
-
-template <class F>
 __global__ void k_field_op(const F* a, const F* b, F* out, size_t n, uint32_t op) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -206,7 +201,7 @@ __global__ void k_field_op(const F* a, const F* b, F* out, size_t n, uint32_t op
         case HK_FOP_SUB: r = x - b[i]; break;
         case HK_FOP_INV: r = x.inverse(); break;
         case HK_FOP_TO_MONT: r = x.to_mont(); break;
-        case HK_FOP_INV_GCD: r = inv_gcd_or_fermat<F>(x, 0); break;
+        case HK_FOP_INV_GCD: r = x.inverse_fast(); break;
         default: r = x.from_mont(); break;
     }
     out[i] = r;
@@ -290,13 +285,30 @@ float time_ms(hk_ctx* ctx, Fn&& fn) {
 
 // ==================================================================================================
 static int32_t ctx_make_side(hk_ctx* ctx) {
-    if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) return HK_ERR_CUDA;
-    if (cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking) != cudaSuccess) return HK_ERR_CUDA;
-    if (cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
-    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
-    if (cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
-    if (cudaEventCreateWithFlags(&ctx->ev_ab, cudaEventDisableTiming) != cudaSuccess) return HK_ERR_CUDA;
+    // numerically lower = higher priority; `least` is what default-priority (caller) streams have
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return HK_ERR_CUDA;
+    auto ev = [](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+    for (int l = 1; l < hk_ctx::LANES; l++) {
+        int bulk = greatest + l < least ? greatest + l : least;
+        if (cudaStreamCreateWithPriority(&ctx->lane_ctl[l], cudaStreamNonBlocking, greatest) != cudaSuccess) return HK_ERR_CUDA;
+        if (cudaStreamCreateWithPriority(&ctx->lane_bulk[l], cudaStreamNonBlocking, bulk) != cudaSuccess) return HK_ERR_CUDA;
+        if (!ev(&ctx->ev_sorted[l]) || !ev(&ctx->ev_accum[l]) || !ev(&ctx->ev_lane_done[l])) return HK_ERR_CUDA;
+    }
+    if (!ev(&ctx->ev_fork)) return HK_ERR_CUDA;
     return HK_OK;
+}
+static void ctx_free_side(hk_ctx* ctx) {
+    for (int l = 1; l < hk_ctx::LANES; l++) {
+        for (cudaStream_t st : {ctx->lane_ctl[l], ctx->lane_bulk[l]})
+            if (st) {
+                cudaStreamSynchronize(st);
+                cudaStreamDestroy(st);
+            }
+        for (cudaEvent_t e : {ctx->ev_sorted[l], ctx->ev_accum[l], ctx->ev_lane_done[l]})
+            if (e) cudaEventDestroy(e);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
 }
 HK_EXPORT int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx** out) {
     if (!out) return HK_ERR_INVALID;
@@ -330,6 +342,7 @@ HK_EXPORT int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx
         ctx->own_stream = true;
     }
     if (ctx_make_side(ctx) != HK_OK) {
+        ctx_free_side(ctx);
         delete ctx;
         return HK_ERR_CUDA;
     }
@@ -345,18 +358,7 @@ HK_EXPORT int32_t hk_ctx_destroy(hk_ctx* ctx) {
     if (ctx->prof_pinned) cudaFreeHost(ctx->prof_pinned);
     ctx->sh.reset();     // shared resources are freed with the last context that references them
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->side) {
-        cudaStreamSynchronize(ctx->side);
-        cudaStreamDestroy(ctx->side);
-    }
-    if (ctx->side2) {
-        cudaStreamSynchronize(ctx->side2);
-        cudaStreamDestroy(ctx->side2);
-    }
-    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    if (ctx->ev_ab) cudaEventDestroy(ctx->ev_ab);
+    ctx_free_side(ctx);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HK_OK;
@@ -385,6 +387,7 @@ HK_EXPORT int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out) {
         ctx->own_stream = true;
     }
     if (ctx_make_side(ctx) != HK_OK) {
+        ctx_free_side(ctx);
         delete ctx;
         return HK_ERR_CUDA;
     }

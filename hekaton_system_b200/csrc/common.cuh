@@ -177,22 +177,27 @@ struct hk_ctx {
     uint32_t curve = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    // helper streams for work that overlaps the main pipeline of a proof batch:
-    //   side  (lane 1): G2 MSM, s*A / r*B1 scalar multiplications, A/B2 normalisation
-    //   side2 (lane 2): witness map (CSR mat-vec + 7 NTTs) and the H MSM
-    cudaStream_t side = nullptr, side2 = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_ab = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    // Lanes of a proof batch (prove.cu).  Lane 0 is the caller's stream.  Every other lane has a
+    // CONTROL stream of the highest priority for its short latency-bound kernels (sort, folds,
+    // reduction, NTT passes) and a BULK stream for its bucket-accumulation kernel, whose priority falls
+    // with the lane number: each accumulation fills the GPU on its own, so the bulk priorities fix the
+    // order in which the block scheduler serves them, while the control kernels of all lanes find
+    // slots as blocks retire and hide under whichever accumulation is running.
+    static constexpr int LANES = 6;
+    cudaStream_t lane_ctl[LANES] = {}, lane_bulk[LANES] = {};
+    cudaEvent_t ev_fork = nullptr, ev_sorted[LANES] = {}, ev_accum[LANES] = {}, ev_lane_done[LANES] = {};
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
     std::shared_ptr<hk::SharedState> sh;
 
     // scratch (grow-only; a context is single-threaded by contract)
-    hk::MsmWs mws[3];                  // one MSM scratch per lane
+    hk::MsmWs mws[LANES];              // one MSM scratch per lane
     hk::DevBuf ws_out;
     hk::DevBuf ws_ntt_tmp, ws_qap[4], ws_io[6], ws_z, ws_misc;
-    cudaStream_t lane_stream(int lane) const { return lane == 0 ? stream : (lane == 1 ? side : side2); }
-    // stream used by the NTT / QAP kernels (normally the main stream; prove_run points it at lane 2)
+    cudaStream_t lane_stream(int lane) const { return lane > 0 && lane < LANES ? lane_ctl[lane] : stream; }
+    cudaStream_t bulk_stream(int lane) const { return lane > 0 && lane < LANES ? lane_bulk[lane] : stream; }
+    // stream used by the NTT / QAP kernels (normally the main stream; prove_run points it at the H lane)
     cudaStream_t qap_stream = nullptr;
     cudaStream_t qstream() const { return qap_stream ? qap_stream : stream; }
     void* pinned = nullptr;

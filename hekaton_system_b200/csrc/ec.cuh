@@ -141,7 +141,7 @@ struct XYZZ {
     __device__ __forceinline__ Affine<F> to_affine() const {
         if (is_inf()) return Affine<F>::inf();
         // 1/ZZ and 1/ZZZ from one inversion: i = 1/(ZZ*ZZZ)
-        F i = (zz * zzz).inverse();
+        F i = (zz * zzz).inverse_fast();
         F izz = i * zzz;
         F izzz = i * zz;
         return {x * izz, y * izzz};

@@ -208,6 +208,10 @@ struct Fp {
         return (raw * rr) * rr;                           // a^-1 R^-1 * R^2 * R^-1 * R^2 * R^-1 = a^-1 R
     }
 
+    // The inverse to use from single-thread / low-occupancy code (affine normalisation in the finish
+    // kernels): ~4x fewer instructions than the Fermat ladder when the warp does not diverge.
+    __device__ __forceinline__ Fp inverse_fast() const { return inverse_gcd(); }
+
     // small-integer constant in Montgomery form (k * R mod p) by repeated addition
     __device__ __forceinline__ static Fp from_small(unsigned k) {
         Fp acc = zero(), o = one();
@@ -244,6 +248,10 @@ struct Fp2T {
     }
     __device__ __forceinline__ Fp2T inverse() const {
         F n = (c0.sqr() + c1.sqr()).inverse();
+        return {c0 * n, (c1 * n).neg()};
+    }
+    __device__ __forceinline__ Fp2T inverse_fast() const {
+        F n = (c0.sqr() + c1.sqr()).inverse_fast();
         return {c0 * n, (c1 * n).neg()};
     }
     __device__ __forceinline__ Fp2T from_mont() const { return {c0.from_mont(), c1.from_mont()}; }

@@ -439,8 +439,10 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     using F = typename GroupFieldT<Curve, GROUP>::F;
     using Fr = typename Curve::Fr;
     Jacobian<F>* d_out = reinterpret_cast<Jacobian<F>*>(d_out_jac_v);
-    cudaStream_t st = ctx->lane_stream(lane);
-    MsmWs& ws = ctx->mws[lane < 0 || lane > 2 ? 0 : lane];
+    if (lane < 0 || lane >= hk_ctx::LANES) lane = 0;
+    cudaStream_t st = ctx->lane_stream(lane);      // control stream: sort, folds, reduction
+    cudaStream_t sb = ctx->bulk_stream(lane);      // the accumulation kernel (== st on lane 0)
+    MsmWs& ws = ctx->mws[lane];
     if (K == 0) return;
     if (n == 0) {
         k_set_identity_jac<F><<<ceil_div(K, 128), 128, 0, st>>>(d_out, K);
@@ -526,10 +528,14 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     k_msm_scatter<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window,
                                                         item_stride, skip, hist, items, keys);
     HK_LAUNCH_CHECK(ctx);
-    int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2, st);
+    if (sb != st) {
+        HK_CUDA(cudaEventRecord(ctx->ev_sorted[lane], st));
+        HK_CUDA(cudaStreamWaitEvent(sb, ctx->ev_sorted[lane], 0));
+    }
+    int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2, sb);
     {
         const dim3 grid(ceil_div(nthr0, 128));
-#define HK_ACC(SS, MB) k_msm_accum<F, SS, MB><<<grid, 128, 0, st>>>(d_bases, items, keys, d_count, buckets, partial, partial_keys, nthr0)
+#define HK_ACC(SS, MB) k_msm_accum<F, SS, MB><<<grid, 128, 0, sb>>>(d_bases, items, keys, d_count, buckets, partial, partial_keys, nthr0)
         if constexpr (GROUP == 2) {
             if (S0 == 32) HK_ACC(32, 1); else if (S0 == 64) HK_ACC(64, 1); else HK_ACC(128, 1);
         } else {
@@ -541,7 +547,11 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
 #undef HK_ACC
     }
     HK_LAUNCH_CHECK(ctx);
-    prof_end(ctx, pi, 0, d_count, st);
+    prof_end(ctx, pi, 0, d_count, sb);
+    if (sb != st) {
+        HK_CUDA(cudaEventRecord(ctx->ev_accum[lane], sb));
+        HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_accum[lane], 0));
+    }
     size_t off = 0;
     for (size_t l = 0; l < lvl_in.size(); l++) {
         uint32_t n_in = lvl_in[l];

@@ -32,9 +32,12 @@ __global__ void k_apply_infinity(Affine<F>* pts, const uint8_t* inf, size_t n) {
     if (inf[i]) pts[i] = Affine<F>::inf();
 }
 
+// `spread` threads per point (only the first of each group works): spread = 32 gives every point its own warp
 template <class F>
-__global__ void k_jac_to_affine(const Jacobian<F>* in, Affine<F>* out, uint8_t* inf, size_t n) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+__global__ void k_jac_to_affine(const Jacobian<F>* in, Affine<F>* out, uint8_t* inf, size_t n, uint32_t spread) {
+    size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g % spread) return;
+    size_t i = g / spread;
     if (i >= n) return;
     XYZZ<F> p = in[i].to_xyzz();
     Affine<F> a = p.to_affine();
@@ -150,18 +153,15 @@ __global__ void k_build_l_scalars(const Fr* __restrict__ z_all, size_t m, size_t
 }
 
 // ---- finish -----------------------------------------------------------------------------------
-// Stage 1 (side stream, overlapped with the L / witness-map / H work): the two scalar multiplications
-// by a fresh point, and the normalisation of A and B2.  One block per proof p.
-//   jacA, jacB1: K each (G1);  jacB2: K (G2);  r, s: K Montgomery Fr.
-//   sab[2p] = s*A, sab[2p+1] = r*B1
+// Stage 1 (highest-priority lane, right after the A and B1 MSMs; overlapped with the bulk MSMs): the two
+// scalar multiplications by a fresh point, and the normalisation of A.  One block per proof p.
+//   jacA, jacB1: K each (G1);  r, s: K Montgomery Fr.   sab[2p] = s*A, sab[2p+1] = r*B1
 template <class Curve>
-__global__ void __launch_bounds__(96)
+__global__ void __launch_bounds__(64)
 k_prove_finish_ab(const Jacobian<typename Curve::Fq>* jacA, const Jacobian<typename Curve::Fq>* jacB1,
-                  const Jacobian<typename Curve::Fq2>* jacB2, const typename Curve::Fr* r_all,
-                  const typename Curve::Fr* s_all, XYZZ<typename Curve::Fq>* sab, Affine<typename Curve::Fq>* outA_all,
-                  Affine<typename Curve::Fq2>* outB_all, uint8_t* inf_all) {
+                  const typename Curve::Fr* r_all, const typename Curve::Fr* s_all, XYZZ<typename Curve::Fq>* sab,
+                  Affine<typename Curve::Fq>* outA_all, uint8_t* inf_all) {
     using Fq = typename Curve::Fq;
-    using Fq2 = typename Curve::Fq2;
     const uint32_t p = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane != 0) return;
@@ -171,25 +171,35 @@ k_prove_finish_ab(const Jacobian<typename Curve::Fq>* jacA, const Jacobian<typen
         sab[2 * p] = scalar_mul<Fq>(a, s.r.v);
         outA_all[p] = a.to_affine();
         inf_all[3 * p + 0] = a.is_inf() ? 1 : 0;
-    } else if (warp == 1) {
+    } else {
         auto r = r_all[p].from_mont();
         sab[2 * p + 1] = scalar_mul<Fq>(jacB1[p].to_xyzz(), r.r.v);
-    } else {
-        XYZZ<Fq2> b = jacB2[p].to_xyzz();
-        outB_all[p] = b.to_affine();
-        inf_all[3 * p + 1] = b.is_inf() ? 1 : 0;
     }
 }
 
-// Stage 2 (main stream, after L' and H): C = s*A + r*B1 + L' + H -> affine.  One thread per proof.
+// Normalisation of B2 (G2), on the lane of the G2 MSM.  One warp per proof (lane 0 works) so the
+// K inversions do not serialise each other's divergent branches.
+template <class Curve>
+__global__ void __launch_bounds__(32)
+k_prove_finish_b2(const Jacobian<typename Curve::Fq2>* jacB2, Affine<typename Curve::Fq2>* outB_all, uint8_t* inf_all) {
+    using Fq2 = typename Curve::Fq2;
+    const uint32_t p = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    XYZZ<Fq2> b = jacB2[p].to_xyzz();
+    outB_all[p] = b.to_affine();
+    inf_all[3 * p + 1] = b.is_inf() ? 1 : 0;
+}
+
+// Stage 2 (main stream, after every lane): C = s*A + r*B1 + L' + H -> affine.  One warp per proof
+// (lane 0 works: the inversion's data-dependent branches must not serialise across proofs).
 template <class Curve>
 __global__ void __launch_bounds__(32)
 k_prove_finish_c(const XYZZ<typename Curve::Fq>* sab, const Jacobian<typename Curve::Fq>* jacL,
                  const Jacobian<typename Curve::Fq>* jacH, Affine<typename Curve::Fq>* outC_all, uint8_t* inf_all,
                  uint32_t K) {
     using Fq = typename Curve::Fq;
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= K) return;
+    const uint32_t p = blockIdx.x;
+    if (p >= K || threadIdx.x != 0) return;
     XYZZ<Fq> c = sab[2 * p];
     c.add(sab[2 * p + 1]);
     c.add(jacL[p].to_xyzz());
@@ -219,17 +229,23 @@ template void apply_infinity<Bls12381>(hk_ctx*, BaseSet&, const uint8_t*);
 template void apply_infinity<Bn254>(hk_ctx*, BaseSet&, const uint8_t*);
 
 template <class Curve, int GROUP>
-void jac_to_affine(hk_ctx* ctx, const void* d_jac, void* d_aff, uint8_t* d_inf, size_t n) {
+void jac_to_affine(hk_ctx* ctx, const void* d_jac, void* d_aff, uint8_t* d_inf, size_t n, cudaStream_t st) {
     using F = typename GroupFieldT<Curve, GROUP>::F;
     if (n == 0) return;
-    k_jac_to_affine<F><<<ceil_div(n, 64), 64, 0, ctx->stream>>>(reinterpret_cast<const Jacobian<F>*>(d_jac),
-                                                                reinterpret_cast<Affine<F>*>(d_aff), d_inf, n);
+    if (!st) st = ctx->stream;
+    // few points: one warp each (the inversion's data-dependent branches do not serialise across points)
+    if (n <= 4096)
+        k_jac_to_affine<F><<<(unsigned)n, 32, 0, st>>>(reinterpret_cast<const Jacobian<F>*>(d_jac),
+                                                       reinterpret_cast<Affine<F>*>(d_aff), d_inf, n, 32);
+    else
+        k_jac_to_affine<F><<<ceil_div(n, 64), 64, 0, st>>>(reinterpret_cast<const Jacobian<F>*>(d_jac),
+                                                           reinterpret_cast<Affine<F>*>(d_aff), d_inf, n, 1);
     HK_LAUNCH_CHECK(ctx);
 }
-template void jac_to_affine<Bls12381, 1>(hk_ctx*, const void*, void*, uint8_t*, size_t);
-template void jac_to_affine<Bls12381, 2>(hk_ctx*, const void*, void*, uint8_t*, size_t);
-template void jac_to_affine<Bn254, 1>(hk_ctx*, const void*, void*, uint8_t*, size_t);
-template void jac_to_affine<Bn254, 2>(hk_ctx*, const void*, void*, uint8_t*, size_t);
+template void jac_to_affine<Bls12381, 1>(hk_ctx*, const void*, void*, uint8_t*, size_t, cudaStream_t);
+template void jac_to_affine<Bls12381, 2>(hk_ctx*, const void*, void*, uint8_t*, size_t, cudaStream_t);
+template void jac_to_affine<Bn254, 1>(hk_ctx*, const void*, void*, uint8_t*, size_t, cudaStream_t);
+template void jac_to_affine<Bn254, 2>(hk_ctx*, const void*, void*, uint8_t*, size_t, cudaStream_t);
 
 template <class Curve, int GROUP>
 void fixed_base_mul(hk_ctx* ctx, const void* d_gen_affine, const Scalar256* d_scalars, size_t n, bool mont,
@@ -372,13 +388,20 @@ void commit_run(hk_ctx* ctx, PkDev& pk, uint32_t stage, size_t K, const uint64_t
     if (K == 0) return;
     const size_t l = pk.r1cs->l;
     const size_t nw = pk.stage_start[stage + 1] - pk.stage_start[stage];
+    // a commitment is a small latency-bound MSM: run it on a prioritised lane so that, when other
+    // contexts keep the GPU busy (proofs of the previous batch), its kernels are served promptly
+    cudaStream_t ls = ctx->lane_ctl[1];
+    HK_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    HK_CUDA(cudaStreamWaitEvent(ls, ctx->ev_fork, 0));
     Fr* sc = ctx->ws_io[0].as<Fr>(K * (nw + 1));
-    k_build_commit_scalars<Fr><<<dim3(ceil_div(nw + 1, 256), (unsigned)K), 256, 0, ctx->stream>>>(
+    k_build_commit_scalars<Fr><<<dim3(ceil_div(nw + 1, 256), (unsigned)K), 256, 0, ls>>>(
         reinterpret_cast<const Fr*>(d_z), z_stride, l + pk.stage_start[stage], nw, reinterpret_cast<const Fr*>(d_kappa), sc);
     HK_LAUNCH_CHECK(ctx);
     Jacobian<Fq>* jac = ctx->ws_out.as<Jacobian<Fq>>(8 * K);
-    msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[stage]), 0, nw + 1, reinterpret_cast<const Scalar256*>(sc), K, true, jac);
-    jac_to_affine<Curve, 1>(ctx, jac, d_out_affine, d_inf, K);
+    msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[stage]), 0, nw + 1, reinterpret_cast<const Scalar256*>(sc), K, true, jac, 0, 1);
+    jac_to_affine<Curve, 1>(ctx, jac, d_out_affine, d_inf, K, ls);
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[1], ls));
+    HK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done[1], 0));
 }
 template void commit_run<Bls12381>(hk_ctx*, PkDev&, uint32_t, size_t, const uint64_t*, size_t, const uint64_t*, void*,
                                    uint8_t*);
@@ -407,28 +430,35 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     Scalar256* Ss = ctx->ws_io[4].as<Scalar256>(K * (m + 2));
     k_build_abc_scalars<Fr><<<dim3(ceil_div(m + 2, 256), Ku), 256, 0, st>>>(z, m, r, s, Sr, Ss);
     HK_LAUNCH_CHECK(ctx);
-    // side lane: the G2 MSM (latency-heavy reduction stages, 3x slower field) overlaps the G1 work
+    // Lanes (common.cuh): every MSM gets its own lane, so all sorts start at once, the accumulation
+    // kernels are served back to back in lane order and each MSM's latency-bound tail (folds, bucket
+    // reduction) hides under the next accumulation.  Order: A and B1 first, because the 5 ms of
+    // two-warp scalar multiplications s*A, r*B1 depend on them and must be hidden under the bulk; then
+    // the G2 MSM (longest tail), the H MSM (half of all additions; its scalars need the witness map,
+    // which runs on the lane's control stream meanwhile), and L' last (shortest tail left exposed).
+    enum { LA = 1, LB1 = 2, LB2 = 3, LH = 4, LL = 5 };
     HK_CUDA(cudaEventRecord(ctx->ev_fork, st));
-    HK_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-    msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, Ss, K, false, jacB2, 0, /*lane=*/1);
-    // main lane
-    msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, Sr, K, false, jac + 0);
-    msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, Ss, K, false, jac + K);
-    // s*A, r*B1 and the normalisation of A, B2: side lane, after A and B1 are available; overlaps L',
-    // the witness map and the H MSM on the main lane
+    for (int ln = 1; ln < hk_ctx::LANES; ln++) HK_CUDA(cudaStreamWaitEvent(ctx->lane_ctl[ln], ctx->ev_fork, 0));
+    msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, Sr, K, false, jac + 0, 0, LA);
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LA], ctx->lane_ctl[LA]));
+    msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, Ss, K, false, jac + K, 0, LB1);
+    // s*A, r*B1 and A's normalisation, on B1's control stream once A is there too
     XYZZ<Fq>* sab = ctx->ws_io[2].as<XYZZ<Fq>>(2 * K);
-    HK_CUDA(cudaEventRecord(ctx->ev_ab, st));
-    HK_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_ab, 0));
-    k_prove_finish_ab<Curve><<<Ku, 96, 0, ctx->side>>>(jac, jac + K, jacB2, r, s, sab, reinterpret_cast<Affine<Fq>*>(d_outA),
-                                                       reinterpret_cast<Affine<Fq2>*>(d_outB), d_inf);
+    HK_CUDA(cudaStreamWaitEvent(ctx->lane_ctl[LB1], ctx->ev_lane_done[LA], 0));
+    k_prove_finish_ab<Curve><<<Ku, 64, 0, ctx->lane_ctl[LB1]>>>(jac, jac + K, r, s, sab,
+                                                                 reinterpret_cast<Affine<Fq>*>(d_outA), d_inf);
     HK_LAUNCH_CHECK(ctx);
-    HK_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
-    // lane 2: witness map and the H MSM need only z -- start them right away
-    HK_CUDA(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork, 0));
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LB1], ctx->lane_ctl[LB1]));
+    // the G2 MSM + B2's normalisation
+    msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, Ss, K, false, jacB2, 0, LB2);
+    k_prove_finish_b2<Curve><<<Ku, 32, 0, ctx->lane_ctl[LB2]>>>(jacB2, reinterpret_cast<Affine<Fq2>*>(d_outB), d_inf);
+    HK_LAUNCH_CHECK(ctx);
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LB2], ctx->lane_ctl[LB2]));
+    // witness map, then the H MSM (they need only z)
     uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N * K);
     uint64_t* h = ctx->ws_qap[1].as<uint64_t>(4 * N * K);
     ntt_domain<Curve>(ctx, log_n);                 // build (and synchronise) the tables before switching streams
-    ctx->qap_stream = ctx->side2;
+    ctx->qap_stream = ctx->lane_ctl[LH];
     try {
         r1cs_evals<Curve>(ctx, *pk.r1cs, d_z_v, abc, K);
         qap_h_from_evals<Curve>(ctx, log_n, abc, h, K);
@@ -438,20 +468,20 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     }
     ctx->qap_stream = nullptr;
     msm_run<Curve, 1>(ctx, msm_view(*pk.h_g), 0, N - 1, reinterpret_cast<const Scalar256*>(h), K, true, jac + 3 * K,
-                      /*sc_stride=*/N, /*lane=*/2);
-    HK_CUDA(cudaEventRecord(ctx->ev_join2, ctx->side2));
-    // main lane: L'
+                      /*sc_stride=*/N, LH);
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LH], ctx->lane_ctl[LH]));
+    // L'
     const size_t nl = pk.stage_start[ns] - pk.stage_start[ns - 1];
     Fr* Ls = ctx->ws_io[1].as<Fr>(K * (nl + ns));
-    k_build_l_scalars<Fr><<<dim3(ceil_div(nl + ns, 256), Ku), 256, 0, st>>>(
+    k_build_l_scalars<Fr><<<dim3(ceil_div(nl + ns, 256), Ku), 256, 0, ctx->lane_ctl[LL]>>>(
         z, m, l + pk.stage_start[ns - 1], nl, r, s, reinterpret_cast<const Fr*>(d_kappas), ns - 1, Ls);
     HK_LAUNCH_CHECK(ctx);
     msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[ns - 1]), 0, nl + ns, reinterpret_cast<const Scalar256*>(Ls), K, true,
-                      jac + 2 * K);
-    HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
-    k_prove_finish_c<Curve><<<ceil_div(K, 32), 32, 0, st>>>(sab, jac + 2 * K, jac + 3 * K,
-                                                            reinterpret_cast<Affine<Fq>*>(d_outC), d_inf, Ku);
+                      jac + 2 * K, 0, LL);
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LL], ctx->lane_ctl[LL]));
+    for (int ln : {LB1, LB2, LH, LL}) HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_lane_done[ln], 0));
+    k_prove_finish_c<Curve><<<Ku, 32, 0, st>>>(sab, jac + 2 * K, jac + 3 * K, reinterpret_cast<Affine<Fq>*>(d_outC), d_inf,
+                                               Ku);
     HK_LAUNCH_CHECK(ctx);
 }
 template void prove_run<Bls12381>(hk_ctx*, PkDev&, size_t, const uint64_t*, const uint64_t*, const uint64_t*,

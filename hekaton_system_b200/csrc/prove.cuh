@@ -20,7 +20,7 @@ struct PkDev {
 template <class Curve>
 void apply_infinity(hk_ctx* ctx, BaseSet& bs, const uint8_t* d_inf);
 template <class Curve, int GROUP>
-void jac_to_affine(hk_ctx* ctx, const void* d_jac, void* d_aff, uint8_t* d_inf, size_t n);
+void jac_to_affine(hk_ctx* ctx, const void* d_jac, void* d_aff, uint8_t* d_inf, size_t n, cudaStream_t st = nullptr);
 template <class Curve, int GROUP>
 void fixed_base_mul(hk_ctx* ctx, const void* d_gen_affine, const Scalar256* d_scalars, size_t n, bool mont,
                     void* d_out_affine);

@@ -66,3 +66,11 @@ def test_fq2_ops(ctx):
     inv = dec(ctx.field_op(B.FIELD_FQ2, B.FOP_INV, A[:50]))
     for x, y in zip(a[:50], inv):
         assert mul(x, y) == (1, 0)
+    inv2 = dec(ctx.field_op(B.FIELD_FQ2, B.FOP_INV_GCD, A[:50]))
+    assert inv2 == inv
+    # edge values through both inverses: 1, p - 1, 2, (p + 1) / 2
+    edge = [1, p - 1, 2, (p + 1) // 2, 3, p - 2]
+    em = codec.to_mont(edge, p, L)
+    for op in (B.FOP_INV, B.FOP_INV_GCD):
+        got = codec.from_mont(ctx.field_op(B.FIELD_FQ, op, em), p)
+        assert got == [pow(x, -1, p) for x in edge]
