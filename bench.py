@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--streams", type=int, default=1,
                     help="concurrent sub-batches per GPU (forked contexts: shared key, own stream + scratch); "
                          "each sub-batch of batch/streams proofs is ONE hk_prove_batch pipeline")
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="batches in flight per GPU: step i runs on pipeline i %% inflight (own contexts, streams and "
+                         "scratch), so the latency-bound tail of one batch overlaps the head of the next")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the standalone MSM / NTT measurements")
     ap.add_argument("--sweep", action="store_true",
@@ -225,12 +228,18 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = Context(args.curve, device=local, stream=stream.cuda_stream)
     nstreams = max(1, min(args.streams, args.batch))
-    wstreams = [stream] + [torch.cuda.Stream(device=local) for _ in range(nstreams - 1)]
-    ctxs = [ctx] + [ctx.fork(stream=s_.cuda_stream) for s_ in wstreams[1:]]
-    # stage-0 commitments of a sub-batch run on their own forked context (own stream + scratch), so the
-    # small latency-bound commitment MSM overlaps the head of the stage-1 proof pipeline
-    cstreams = [torch.cuda.Stream(device=local) for _ in range(nstreams)]
-    cctxs = [ctx.fork(stream=s_.cuda_stream) for s_ in cstreams]
+    inflight = max(1, args.inflight)
+    # pipelines: each has, per sub-batch, a proof context and a commitment context (forks of `ctx`: shared
+    # keys, own stream + scratch).  Stage-0 commitments run on their own context so the small latency-bound
+    # commitment MSM overlaps the head of the stage-1 proof pipeline.
+    pipes = []
+    for _ in range(inflight):
+        ps = [torch.cuda.Stream(device=local) for _ in range(nstreams)]
+        cs = [torch.cuda.Stream(device=local) for _ in range(nstreams)]
+        pipes.append(dict(pstreams=ps, cstreams=cs, ctxs=[ctx.fork(stream=s_.cuda_stream) for s_ in ps],
+                          cctxs=[ctx.fork(stream=s_.cuda_stream) for s_ in cs]))
+    all_ctxs = [c_ for pp in pipes for c_ in pp["ctxs"] + pp["cctxs"]]
+    all_streams = [s_ for pp in pipes for s_ in pp["pstreams"] + pp["cstreams"]]
     cv = ctx.curve
     t0 = time.time()
     wl = workload.make_workload(cv, args.shape, seed=1, num_assignments=2)
@@ -244,8 +253,8 @@ def main():
                           f"N=2^{wl.log_n}, {args.curve}, bit-heavy witnesses",
               "subcircuits_per_gpu_per_step": args.batch, "global_batch": args.batch * world,
               "parallelism": f"subcircuits sharded over {world} GPU(s), no data-path collective; "
-                             f"{nstreams} sub-batch(es) of {args.batch // nstreams} proofs in flight per GPU "
-                             f"(hk_prove_batch on forked contexts)",
+                             f"{inflight} batch(es) in flight per GPU, each {nstreams} sub-batch(es) of "
+                             f"{args.batch // nstreams} proofs (hk_commit_batch + hk_prove_batch on forked contexts)",
               "l2": "working set (resident bases ~150 MB + MSM workspaces) exceeds the 126 MB L2",
               "setup_s": round(setup_s, 1)}
 
@@ -295,47 +304,57 @@ def main():
         hz = hz.reshape(len(its), -1, 4)
         dz = torch.from_numpy(hz.view(np.int64)).to(dev)
         drsk = torch.from_numpy(np.concatenate([hr.ravel(), hs.ravel(), hk_.ravel()]).view(np.int64)).to(dev)
-        out = torch.zeros((per * (OUTB + COMB) + 63) // 8 + 4, dtype=torch.int64, device=dev)
-        chunks.append(dict(hz=hz, hr=hr, hs=hs, hk=hk_, dz=dz, drsk=drsk, out=out, pins=pins))
+        outs = [torch.zeros((per * (OUTB + COMB) + 63) // 8 + 4, dtype=torch.int64, device=dev) for _ in range(inflight)]
+        chunks.append(dict(hz=hz, hr=hr, hs=hs, hk=hk_, dz=dz, drsk=drsk, outs=outs, pins=pins))
     my_subcircuits = shard_range(args.batch * world, world, rank)      # contiguous chunk per rank (node.rs:471-493)
     assert len(my_subcircuits) == args.batch
 
-    def step_device():
-        # fan out: every worker stream starts after the main stream, the main stream joins them all
-        for ws in wstreams[1:] + cstreams:
-            ws.wait_stream(stream)
+    def step_device(i):
+        # asynchronous: everything is enqueued on the pipeline's own streams (in order per context)
+        pp = pipes[i % inflight]
         for t, ch in enumerate(chunks):
             q = ch["drsk"].data_ptr()
-            p = ch["out"].data_ptr()
+            p = ch["outs"][i % inflight].data_ptr()
             pc = p + ((per * OUTB + 15) // 16) * 16
             # stage 0: commitments (committer.rs:55-98); stage 1: proofs (committer.rs:100-122)
-            cctxs[t].commit_batch_device(pk.handle, 0, per, ch["dz"].data_ptr(), wl.m, q + 64 * per, pc, pc + per * P1)
-            ctxs[t].prove_batch_device(pk.handle, per, ch["dz"].data_ptr(), q, q + 32 * per, q + 64 * per,
-                                       p, p + per * P1, p + per * (P1 + P2), p + per * (2 * P1 + P2))
-        for ws in wstreams[1:] + cstreams:
-            stream.wait_stream(ws)
+            pp["cctxs"][t].commit_batch_device(pk.handle, 0, per, ch["dz"].data_ptr(), wl.m, q + 64 * per, pc, pc + per * P1)
+            pp["ctxs"][t].prove_batch_device(pk.handle, per, ch["dz"].data_ptr(), q, q + 32 * per, q + 64 * per,
+                                             p, p + per * P1, p + per * (P1 + P2), p + per * (2 * P1 + P2))
         if world > 1:
-            # the path's one exchange step: proof records to every rank (aggregation input)
-            gather_records(torch.cat([ch["out"] for ch in chunks]).view(1, -1), world)
+            # the path's one exchange step: proof records to every rank (aggregation input), on the
+            # pipeline's first stream once its other streams are done
+            s0 = pp["pstreams"][0]
+            for s_ in pp["pstreams"][1:] + pp["cstreams"]:
+                s0.wait_stream(s_)
+            with torch.cuda.stream(s0):
+                gather_records(torch.cat([ch["outs"][i % inflight] for ch in chunks]).view(1, -1), world)
 
     import threading
 
-    def step_host():
-        # one host thread per context, like the reference's per-proof OS threads (node.rs:745-795);
-        # each call copies its assignments H2D, proves the sub-batch, and copies the proofs back
-        res = [None] * (2 * nstreams)
+    def run_device(steps):
+        for s_ in all_streams:
+            s_.wait_stream(stream)
+        for i in range(steps):
+            step_device(i)
+        for s_ in all_streams:
+            stream.wait_stream(s_)
 
-        def work(j):
-            t, ch = j // 2, chunks[j // 2]
-            if j % 2 == 0:
-                res[j] = cctxs[t].commit_batch(pk.handle, 0, ch["hz"], ch["hk"])
-            else:
-                res[j] = ctxs[t].prove_batch(pk.handle, ch["hz"], ch["hr"], ch["hs"], ch["hk"], pinned=True)
+    def run_host(steps):
+        # host threads like the reference's per-proof OS threads (node.rs:745-795): per pipeline and
+        # sub-batch one thread for the commitments and one for the proofs; every call copies its
+        # inputs H2D from pinned memory, computes, and copies the result back (blocking)
+        def work(j, t, kind):
+            pp, ch = pipes[j], chunks[t]
+            for _ in range(j, steps, inflight):
+                if kind == 0:
+                    pp["cctxs"][t].commit_batch(pk.handle, 0, ch["hz"], ch["hk"])
+                else:
+                    pp["ctxs"][t].prove_batch(pk.handle, ch["hz"], ch["hr"], ch["hs"], ch["hk"], pinned=True)
 
-        ths = [threading.Thread(target=work, args=(j,)) for j in range(2 * nstreams)]
+        ths = [threading.Thread(target=work, args=(j, t, kind)) for j in range(inflight) for t in range(nstreams)
+               for kind in (0, 1)]
         [t.start() for t in ths]
         [t.join() for t in ths]
-        return res
 
     def timed(fn, steps):
         if world > 1:
@@ -343,8 +362,7 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
-            fn()
+        fn(steps)
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -370,13 +388,12 @@ def main():
 
     imad_peak = ctx.bench_imad_wide(8192)          # wide multiply-accumulates / s (roofline denominator)
 
-    for _ in range(args.warmup):
-        step_device()
+    run_device(args.warmup)
     torch.cuda.synchronize()
     if args.timeline:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as tp:
-            step_device()
+            run_device(inflight)
             torch.cuda.synchronize()
         tmp = args.timeline + ".chrome.json"
         tp.export_chrome_trace(tmp)
@@ -392,23 +409,22 @@ def main():
         ctx.close()
         return 0
     sampler = ClockSampler(local) if rank == 0 else None
-    for c_ in ctxs + cctxs:
+    for c_ in all_ctxs:
         c_.profile_reset()
         c_.profile(True)
-    l0 = sum(c_.launches for c_ in ctxs + cctxs)
-    ms_dev = timed(step_device, args.steps)
-    launches = sum(c_.launches for c_ in ctxs + cctxs) - l0
+    l0 = sum(c_.launches for c_ in all_ctxs)
+    ms_dev = timed(run_device, args.steps)
+    launches = sum(c_.launches for c_ in all_ctxs) - l0
     prof = {}
     for k in (0, 1, 2):
-        rs = [c_.profile_read(k) for c_ in ctxs + cctxs]
+        rs = [c_.profile_read(k) for c_ in all_ctxs]
         prof[k] = tuple(sum(x[j] for x in rs) for j in range(3))
-    for c_ in ctxs + cctxs:
+    for c_ in all_ctxs:
         c_.profile(False)
         c_.profile_reset()
     # end-to-end through the host-buffer C-ABI call
-    for _ in range(min(args.warmup, 2)):
-        step_host()
-    ms_e2e = timed(step_host, args.steps)
+    run_host(min(args.warmup, 2) * inflight)
+    ms_e2e = timed(run_host, args.steps)
     clocks = sampler.stop() if sampler else None
 
     # secondary headline figures (BASELINE.json metric: "G1 MSM Mpts/s at 2^20"; north_star: MSM / NTT
@@ -472,7 +488,7 @@ def main():
             "verified_vs_trapdoor": verified,
         }
         print(json.dumps(line))
-    for c_ in ctxs[1:] + cctxs:
+    for c_ in all_ctxs:
         c_.close()
     ctx.close()
     if world > 1:

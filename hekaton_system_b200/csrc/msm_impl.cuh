@@ -97,44 +97,77 @@ __global__ void k_scalars_from_mont(const Scalar256* in, Scalar256* out, size_t 
 //   item = w * item_stride + i                                      item_stride = 0 / n_total
 // The K scalar vectors of a batch share the bases, so the batch index is just another bucket-set
 // dimension; `sc_stride` is the distance (in scalars) between consecutive vectors.
+// Both sort kernels aggregate their atomics per warp: lanes whose current digit falls into the same
+// bucket are found with match.any, one lane issues a single atomic for the group.  Witness vectors of
+// SHA-256 / Poseidon circuits are mostly bits (45 % of all scalars are 1), so without this almost half of
+// the atomics of a launch hit the same few addresses and serialise in L2.
 static __global__ void k_msm_hist(const Scalar256* sc, size_t n, size_t K, size_t sc_stride, int c, int W, uint32_t B,
                                   uint32_t sets_per_vec, uint32_t per_window, const uint8_t* __restrict__ skip,
                                   uint32_t* hist) {
     size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (g >= n * K) return;
-    size_t k = g / n, i = g - k * n;
-    if (skip && skip[i]) return;          // base at infinity contributes nothing
-    const Scalar256* p = sc + k * sc_stride + i;
-    uint64_t s[4] = {p->v[0], p->v[1], p->v[2], p->v[3]};
-    if ((s[0] | s[1] | s[2] | s[3]) == 0) return;
+    const unsigned lane = threadIdx.x & 31u;
+    bool active = g < n * K;
+    size_t k = 0, i = 0;
+    uint64_t s[4] = {0, 0, 0, 0};
+    if (active) {
+        k = g / n;
+        i = g - k * n;
+        if (skip && skip[i]) active = false;          // base at infinity contributes nothing
+    }
+    if (active) {
+        const Scalar256* p = sc + k * sc_stride + i;
+        s[0] = p->v[0], s[1] = p->v[1], s[2] = p->v[2], s[3] = p->v[3];
+        active = (s[0] | s[1] | s[2] | s[3]) != 0;
+    }
+    if (!__any_sync(0xffffffffu, active)) return;
     uint32_t carry = 0;
     const size_t base = k * sets_per_vec;
     for (int w = 0; w < W; w++) {
-        int d = msm_digit(s, w, c, W, carry);
-        if (d != 0) atomicAdd(&hist[(base + (size_t)w * per_window) * B + (uint32_t)(abs(d) - 1)], 1u);
+        int d = active ? msm_digit(s, w, c, W, carry) : 0;
+        const unsigned amask = __ballot_sync(0xffffffffu, d != 0);
+        if (d != 0) {
+            uint32_t key = (uint32_t)((base + (size_t)w * per_window) * B) + (uint32_t)(abs(d) - 1);
+            unsigned peers = __match_any_sync(amask, key);
+            if (lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+        }
     }
 }
 
+// pairs[pos] = key << 32 | item: the accumulation kernel reads one 8-byte stream instead of two 4-byte ones
 static __global__ void k_msm_scatter(const Scalar256* sc, size_t n, size_t K, size_t sc_stride, int c, int W, uint32_t B,
                                      uint32_t sets_per_vec, uint32_t per_window, uint32_t item_stride,
-                                     const uint8_t* __restrict__ skip, uint32_t* cursor, uint32_t* items,
-                                     uint32_t* keys) {
+                                     const uint8_t* __restrict__ skip, uint32_t* cursor, uint64_t* pairs) {
     size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (g >= n * K) return;
-    size_t k = g / n, i = g - k * n;
-    if (skip && skip[i]) return;
-    const Scalar256* p = sc + k * sc_stride + i;
-    uint64_t s[4] = {p->v[0], p->v[1], p->v[2], p->v[3]};
-    if ((s[0] | s[1] | s[2] | s[3]) == 0) return;
+    const unsigned lane = threadIdx.x & 31u;
+    bool active = g < n * K;
+    size_t k = 0, i = 0;
+    uint64_t s[4] = {0, 0, 0, 0};
+    if (active) {
+        k = g / n;
+        i = g - k * n;
+        if (skip && skip[i]) active = false;
+    }
+    if (active) {
+        const Scalar256* p = sc + k * sc_stride + i;
+        s[0] = p->v[0], s[1] = p->v[1], s[2] = p->v[2], s[3] = p->v[3];
+        active = (s[0] | s[1] | s[2] | s[3]) != 0;
+    }
+    if (!__any_sync(0xffffffffu, active)) return;
     uint32_t carry = 0;
     const size_t base = k * sets_per_vec;
     for (int w = 0; w < W; w++) {
-        int d = msm_digit(s, w, c, W, carry);
+        int d = active ? msm_digit(s, w, c, W, carry) : 0;
+        const unsigned amask = __ballot_sync(0xffffffffu, d != 0);
         if (d != 0) {
             uint32_t key = (uint32_t)((base + (size_t)w * per_window) * B) + (uint32_t)(abs(d) - 1);
-            uint32_t pos = atomicAdd(&cursor[key], 1u);
-            items[pos] = (((uint32_t)w * item_stride + (uint32_t)i) << 1) | (d < 0 ? 1u : 0u);
-            keys[pos] = key;
+            unsigned peers = __match_any_sync(amask, key);
+            const int leader = __ffs(peers) - 1;
+            uint32_t pos0 = 0;
+            if ((int)lane == leader) pos0 = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+            pos0 = __shfl_sync(peers, pos0, leader);
+            uint32_t pos = pos0 + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            uint32_t item = (((uint32_t)w * item_stride + (uint32_t)i) << 1) | (d < 0 ? 1u : 0u);
+            pairs[pos] = ((uint64_t)key << 32) | item;
         }
     }
 }
@@ -227,9 +260,9 @@ static constexpr uint32_t KEY_NONE = 0xffffffffu;
 
 template <class F, int S, int MINB>
 __global__ void __launch_bounds__(128, MINB)
-k_msm_accum(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ items,
-            const uint32_t* __restrict__ keys, const uint32_t* __restrict__ d_count, XYZZ<F>* buckets,
-            XYZZ<F>* partial, uint32_t* partial_keys, uint32_t nthreads) {
+k_msm_accum(const Affine<F>* __restrict__ bases, const uint64_t* __restrict__ pairs,
+            const uint32_t* __restrict__ d_count, XYZZ<F>* buckets, XYZZ<F>* partial, uint32_t* partial_keys,
+            uint32_t nthreads) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
     uint32_t count = *d_count;
@@ -237,12 +270,13 @@ k_msm_accum(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ it
     uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
     if (lo < count) {
         size_t hi = lo + S < count ? lo + S : count;
-        uint32_t cur = keys[lo];
+        uint32_t cur = (uint32_t)(pairs[lo] >> 32);
         uint32_t first_key = cur;
         XYZZ<F> acc = XYZZ<F>::inf();
         bool first_done = false;
         for (size_t i = lo; i < hi; i++) {
-            uint32_t k = keys[i];
+            const uint64_t pr = pairs[i];
+            uint32_t k = (uint32_t)(pr >> 32);
             if (k != cur) {
                 if (!first_done) {
                     partial[2 * (size_t)t] = acc;
@@ -253,7 +287,7 @@ k_msm_accum(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ it
                 acc = XYZZ<F>::inf();
                 cur = k;
             }
-            uint32_t it = items[i];
+            uint32_t it = (uint32_t)pr;
             Affine<F> p = bases[it >> 1];
             acc.madd(p, it & 1);
         }
@@ -490,8 +524,7 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     }
     uint32_t* hist = ws.hist.as<uint32_t>(nkeys + 4);
     uint32_t* d_count = hist + nkeys;     // total item count lives right after the histogram
-    uint32_t* items = ws.items.as<uint32_t>(2 * max_items);
-    uint32_t* keys = items + max_items;
+    uint64_t* pairs = ws.items.as<uint64_t>(max_items);
     XYZZ<F>* buckets = ws.buckets.as<XYZZ<F>>(nkeys);
     const uint32_t nthr0 = ceil_div(max_items, S0);
     std::vector<uint32_t> lvl_in;      // entries consumed at fold level l
@@ -526,7 +559,7 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     HK_LAUNCH_CHECK(ctx);
     exclusive_scan_u32(ctx, ws, st, hist, nkeys, d_count);
     k_msm_scatter<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window,
-                                                        item_stride, skip, hist, items, keys);
+                                                        item_stride, skip, hist, pairs);
     HK_LAUNCH_CHECK(ctx);
     if (sb != st) {
         HK_CUDA(cudaEventRecord(ctx->ev_sorted[lane], st));
@@ -535,7 +568,7 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2, sb);
     {
         const dim3 grid(ceil_div(nthr0, 128));
-#define HK_ACC(SS, MB) k_msm_accum<F, SS, MB><<<grid, 128, 0, sb>>>(d_bases, items, keys, d_count, buckets, partial, partial_keys, nthr0)
+#define HK_ACC(SS, MB) k_msm_accum<F, SS, MB><<<grid, 128, 0, sb>>>(d_bases, pairs, d_count, buckets, partial, partial_keys, nthr0)
         if constexpr (GROUP == 2) {
             if (S0 == 32) HK_ACC(32, 1); else if (S0 == 64) HK_ACC(64, 1); else HK_ACC(128, 1);
         } else {

@@ -53,7 +53,7 @@ struct FrConsts<Bn254> {
 
 static constexpr uint32_t NTT_TMAX = 11;   // tile = 2^11 elements = 64 KiB of shared memory
 static constexpr uint32_t NTT_QMAX = 2;
-static constexpr uint32_t NTT_TPB = 512;
+static constexpr uint32_t NTT_TPB = 256;   // one radix-8 group per thread and round on a full tile
 
 enum : uint32_t { NTT_PERM_IN = 1, NTT_PERM_OUT = 2 };
 
@@ -100,9 +100,14 @@ inline std::vector<NttPass> ntt_plan(uint32_t log_n) {
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return bits ? (__brev(x) >> (32 - bits)) : 0; }
 
-// shared-memory element access: two planes of 16-byte halves
+// shared-memory element access: two planes of 16-byte halves.  The element index is swizzled
+// (e ^ ((e >> 3) & 7)) so that both the unit-stride accesses of the load/store phases and the
+// power-of-two-strided accesses of the register-radix rounds spread over all banks: the 8 threads of a
+// quarter-warp always touch 8 different 16-byte bank groups.
+__device__ __forceinline__ uint32_t sm_swz(uint32_t e) { return e ^ ((e >> 3) & 7u); }
 template <class Fr>
 __device__ __forceinline__ Fr sm_load(const uint4* lo, const uint4* hi, uint32_t e) {
+    e = sm_swz(e);
     uint4 a = lo[e], b = hi[e];
     Fr x;
     x.r.v[0] = (uint64_t)a.x | ((uint64_t)a.y << 32);
@@ -113,13 +118,77 @@ __device__ __forceinline__ Fr sm_load(const uint4* lo, const uint4* hi, uint32_t
 }
 template <class Fr>
 __device__ __forceinline__ void sm_store(uint4* lo, uint4* hi, uint32_t e, const Fr& x) {
+    e = sm_swz(e);
     lo[e] = make_uint4((uint32_t)x.r.v[0], (uint32_t)(x.r.v[0] >> 32), (uint32_t)x.r.v[1], (uint32_t)(x.r.v[1] >> 32));
     hi[e] = make_uint4((uint32_t)x.r.v[2], (uint32_t)(x.r.v[2] >> 32), (uint32_t)x.r.v[3], (uint32_t)(x.r.v[3] >> 32));
 }
 
+// tile element e -> global index (see k_ntt_pass)
+struct NttTileMap {
+    uint32_t q, k, L, hs_bits, block;
+    __device__ __forceinline__ uint32_t operator()(uint32_t e) const {
+        uint32_t lq = e & ((1u << q) - 1);
+        uint32_t m = (e >> q) & ((1u << k) - 1);
+        uint32_t hsub = e >> (q + k);
+        uint32_t outer = (block << hs_bits) | hsub;
+        uint32_t lhi = outer & ((1u << (L - q)) - 1);
+        uint32_t H = outer >> (L - q);
+        return (H << (k + L)) | (m << L) | (lhi << q) | lq;
+    }
+};
+
+// One register-radix round: R consecutive butterfly stages on groups of 2^R tile elements that differ
+// in tile bits [pos_lo, pos_lo + R).  A group is loaded from shared memory once, its R * 2^(R-1)
+// butterflies run in registers (2^(R-1) independent multiplications per stage keep the multiplier pipe
+// busy from a single warp), and it is stored once: one shared-memory round trip and one barrier per
+// R stages instead of per stage.  The stage acting on tile bit p is stage t = k - 1 - (p - q) of the
+// pass (global stage s0 + t); its twiddle index is the global index of the butterfly's lower element
+// modulo 2^(L + p - q).  DIF walks the bits downwards, DIT upwards.
+template <class Fr, bool DIT, int R>
+__device__ __forceinline__ void ntt_round(uint4* slo, uint4* shi, const Fr* __restrict__ tw, size_t N,
+                                          const NttTileMap& map, uint32_t s0, uint32_t tile, uint32_t pos_lo) {
+    constexpr int GS = 1 << R;
+    const uint32_t ngroups = tile >> R;
+    for (uint32_t g = threadIdx.x; g < ngroups; g += blockDim.x) {
+        const uint32_t base = ((g >> pos_lo) << (pos_lo + R)) | (g & ((1u << pos_lo) - 1));
+        Fr x[GS];
+#pragma unroll
+        for (int c = 0; c < GS; c++) x[c] = sm_load<Fr>(slo, shi, base + ((uint32_t)c << pos_lo));
+        const uint32_t ibase = map(base);
+        const uint32_t g_lo = map.L + (pos_lo - map.q);         // global bit of tile bit pos_lo
+#pragma unroll
+        for (int aa = 0; aa < R; aa++) {
+            const int a = DIT ? aa : (R - 1 - aa);              // bit within the group
+            const uint32_t gb = g_lo + a;                       // global bit toggled by this stage
+            const uint32_t t = map.k - 1 - (pos_lo + a - map.q);
+            const size_t off_s = N - (N >> (s0 + t));
+            const uint32_t jb = ibase & ((1u << gb) - 1);
+#pragma unroll
+            for (int lowb = 0; lowb < (1 << a); lowb++) {
+                const Fr w = tw[off_s + jb + ((uint32_t)lowb << g_lo)];
+#pragma unroll
+                for (int hi = 0; hi < (1 << (R - 1 - a)); hi++) {
+                    const int c0 = (hi << (a + 1)) | lowb, c1 = c0 | (1 << a);
+                    if (DIT) {
+                        Fr v = x[c1] * w;
+                        x[c1] = x[c0] - v;
+                        x[c0] = x[c0] + v;
+                    } else {
+                        Fr u = x[c0];
+                        x[c0] = u + x[c1];
+                        x[c1] = (u - x[c1]) * w;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < GS; c++) sm_store(slo, shi, base + ((uint32_t)c << pos_lo), x[c]);
+    }
+}
+
 // One pass.  grid = (N >> T, K).  in/out may alias when no permutation flag is set.
 template <class Fr, bool DIT>
-__global__ void __launch_bounds__(NTT_TPB, 2)      // <= 64 registers: 2-3 CTAs (32-48 warps) per SM -- profiles/r01c
+__global__ void __launch_bounds__(NTT_TPB, 2)
 k_ntt_pass(const Fr* in_all, Fr* out_all, const Fr* __restrict__ tw, uint32_t log_n,
            uint32_t s0, uint32_t k, uint32_t q, uint32_t T, const Fr* __restrict__ pre_scale,
            const Fr* __restrict__ post_scale, const Fr* __restrict__ post_const, uint32_t flags) {
@@ -130,18 +199,8 @@ k_ntt_pass(const Fr* in_all, Fr* out_all, const Fr* __restrict__ tw, uint32_t lo
     const Fr* in = in_all + (size_t)blockIdx.y * N;
     Fr* out = out_all + (size_t)blockIdx.y * N;
     const uint32_t L = log_n - s0 - k;
-    const uint32_t hs_bits = T - k - q;
     const uint32_t tile = 1u << T;
-
-    auto gidx = [&](uint32_t e) -> uint32_t {
-        uint32_t lq = e & ((1u << q) - 1);
-        uint32_t m = (e >> q) & ((1u << k) - 1);
-        uint32_t hsub = e >> (q + k);
-        uint32_t outer = (blockIdx.x << hs_bits) | hsub;
-        uint32_t lhi = outer & ((1u << (L - q)) - 1);
-        uint32_t H = outer >> (L - q);
-        return (H << (k + L)) | (m << L) | (lhi << q) | lq;
-    };
+    const NttTileMap gidx{q, k, L, T - k - q, blockIdx.x};
 
     for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
         uint32_t i = gidx(e);
@@ -152,31 +211,17 @@ k_ntt_pass(const Fr* in_all, Fr* out_all, const Fr* __restrict__ tw, uint32_t lo
     }
     __syncthreads();
 
-    const uint32_t nbf = tile >> 1;
-    for (uint32_t tt = 0; tt < k; tt++) {
-        const uint32_t t = DIT ? (k - 1 - tt) : tt;      // stage offset within the pass
-        const uint32_t s = s0 + t;
-        const uint32_t mb = k - 1 - t;                    // bit of m toggled by this stage
-        const uint32_t pos = q + mb;
-        const size_t off_s = N - (N >> s);
-        for (uint32_t bf = threadIdx.x; bf < nbf; bf += blockDim.x) {
-            uint32_t e0 = ((bf >> pos) << (pos + 1)) | (bf & ((1u << pos) - 1));
-            uint32_t e1 = e0 | (1u << pos);
-            uint32_t i0 = gidx(e0);
-            uint32_t j = i0 & ((1u << (L + mb)) - 1);
-            Fr w = tw[off_s + j];
-            Fr u = sm_load<Fr>(slo, shi, e0);
-            Fr v = sm_load<Fr>(slo, shi, e1);
-            if (DIT) {
-                v = v * w;
-                sm_store(slo, shi, e0, u + v);
-                sm_store(slo, shi, e1, u - v);
-            } else {
-                sm_store(slo, shi, e0, u + v);
-                sm_store(slo, shi, e1, (u - v) * w);
-            }
-        }
+    // the k stages act on tile bits [q, q + k): DIF from the top bit down, DIT from the bottom bit up,
+    // three bits (one radix-8 round) at a time
+    uint32_t done = 0;
+    while (done < k) {
+        const uint32_t R = (k - done >= 3) ? 3 : (k - done);
+        const uint32_t pos_lo = DIT ? (q + done) : (q + k - done - R);
+        if (R == 3) ntt_round<Fr, DIT, 3>(slo, shi, tw, N, gidx, s0, tile, pos_lo);
+        else if (R == 2) ntt_round<Fr, DIT, 2>(slo, shi, tw, N, gidx, s0, tile, pos_lo);
+        else ntt_round<Fr, DIT, 1>(slo, shi, tw, N, gidx, s0, tile, pos_lo);
         __syncthreads();
+        done += R;
     }
 
     Fr pc;
