@@ -59,6 +59,11 @@ def parse():
     return ap.parse_args()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of k_msm_accum<G1> per mixed addition, from the committed
+# `ncu --set full` capture (profiles/r01c_accum_setfull_raw.csv: 3.79 GB, 16.8 M additions)
+NCU_ACCUM_DRAM_BYTES_PER_ADD = 3.79e9 / 16.8e6
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -188,8 +193,22 @@ def measure_extras(ctx, stream, imad_peak, hbm_gbs):
     return out
 
 
+def emit(line):
+    """The one JSON line goes to the REAL stdout; everything else (library banners such as NCCL's version
+    line, build output) was redirected to stderr at start-up."""
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    if not args.sweep:
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)              # fd 1 -> stderr for the rest of the process (C libraries included)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -276,7 +295,7 @@ def main():
         v = args.steps / dt
         sample = (f"{args.steps} subcircuit(s) (commit + prove) of the same workload, one per step "
                   f"(bounded sample of the {args.batch}-subcircuit step)")
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "subcircuit proofs/s", "value": v, "unit": "proofs/s", "n_gpus": 0,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Montgomery, 64-bit limbs)",
@@ -409,19 +428,43 @@ def main():
         ctx.close()
         return 0
     sampler = ClockSampler(local) if rank == 0 else None
-    for c_ in all_ctxs:
-        c_.profile_reset()
-        c_.profile(True)
     l0 = sum(c_.launches for c_ in all_ctxs)
     ms_dev = timed(run_device, args.steps)
     launches = sum(c_.launches for c_ in all_ctxs) - l0
-    prof = {}
-    for k in (0, 1, 2):
-        rs = [c_.profile_read(k) for c_ in all_ctxs]
-        prof[k] = tuple(sum(x[j] for x in rs) for j in range(3))
-    for c_ in all_ctxs:
-        c_.profile(False)
-        c_.profile_reset()
+    # Roofline pass: the same step once more with the profiling events on, (a) as it runs in the pipeline
+    # (launches of different lanes / batches overlap and share the GPU) and (b) with the lanes of ONE batch
+    # serialised, so that every launch of the dominant kernels is timed alone.  Outside the timed region:
+    # the event records and the device-counter read-backs perturb the pipeline.
+    def profiled(serial, steps):
+        cs = [pipes[0]["ctxs"][0], pipes[0]["cctxs"][0]] if serial else all_ctxs
+        for c_ in cs:
+            c_.profile_reset()
+            c_.profile(True, serial=serial)
+        if serial:
+            for s_ in all_streams:
+                s_.wait_stream(stream)
+            q, p_ = chunks[0]["drsk"].data_ptr(), chunks[0]["outs"][0].data_ptr()
+            pc_ = p_ + ((per * OUTB + 15) // 16) * 16
+            for _ in range(steps):
+                cs[1].commit_batch_device(pk.handle, 0, per, chunks[0]["dz"].data_ptr(), wl.m, q + 64 * per, pc_, pc_ + per * P1)
+                torch.cuda.synchronize()
+                cs[0].prove_batch_device(pk.handle, per, chunks[0]["dz"].data_ptr(), q, q + 32 * per, q + 64 * per,
+                                         p_, p_ + per * P1, p_ + per * (P1 + P2), p_ + per * (2 * P1 + P2))
+                torch.cuda.synchronize()
+            ms = None
+        else:
+            ms = timed(run_device, steps)
+        out = {}
+        for k in (0, 1, 2):
+            rs = [c_.profile_read(k) for c_ in cs]
+            out[k] = tuple(sum(x[j] for x in rs) for j in range(3))
+        for c_ in cs:
+            c_.profile(False)
+            c_.profile_reset()
+        return out, ms
+
+    prof, ms_prof = profiled(False, max(2, min(args.steps, 4)))
+    prof_alone, _ = profiled(True, 2)
     # end-to-end through the host-buffer C-ABI call
     run_host(min(args.warmup, 2) * inflight)
     ms_e2e = timed(run_host, args.steps)
@@ -444,24 +487,40 @@ def main():
         # (2 N^2 + N) wide MACs, N = 2 * fq_limbs 32-bit limbs  
         n32 = 2 * L
         macs_per_add = 10 * (2 * n32 * n32 + n32)
-        ms_acc, n_acc, adds = prof[0]
+        ms_acc, n_acc, adds = prof_alone[0]
+        ms_acc_p, n_acc_p, adds_p = prof[0]
         roof = None
         if n_acc:
             ach = adds * macs_per_add / (ms_acc * 1e-3)
             roof = {"kernel": "k_msm_accum<G1>", "bound": "imad", "achieved": ach / 1e12, "peak": imad_peak / 1e12,
-                    "unit": "T wide-MAC/s (32x32+64 IMAD.WIDE)", "frac": ach / imad_peak, "traffic": None,
-                    "launches": n_acc, "avg_launch_ms": ms_acc / n_acc, "share_of_step": ms_acc / ms_dev,
-                    "note": "durations are per launch on its own stream; with several proofs in flight launches "
-                            "overlap, so achieved is a per-launch figure and share_of_step is summed kernel time / wall time",
+                    "unit": "T wide-MAC/s (32x32+64 IMAD.WIDE)", "frac": ach / imad_peak,
+                    "traffic": NCU_ACCUM_DRAM_BYTES_PER_ADD * adds / n_acc,
+                    "traffic_note": f"dram read+write bytes per launch = {NCU_ACCUM_DRAM_BYTES_PER_ADD:.0f} B per addition "
+                                    "(ncu --set full capture of this kernel, profiles/: 3.79 GB for a launch of 16.8 M "
+                                    "additions) x this run's additions per launch; algorithmic = 104 B per addition "
+                                    "(one 96-B affine base + one 8-B sorted pair)",
+                    "launches": n_acc, "avg_launch_ms": ms_acc / n_acc, "units_per_launch": adds / n_acc,
+                    "algorithmic_macs_per_unit": macs_per_add,
+                    "share_of_step": (ms_acc_p / ms_prof) if ms_prof else None,
+                    "in_pipeline": {"frac": (adds_p * macs_per_add / (ms_acc_p * 1e-3) / imad_peak) if n_acc_p else None,
+                                    "launches": n_acc_p, "avg_launch_ms": (ms_acc_p / n_acc_p) if n_acc_p else None},
+                    "note": "frac: CUDA events around every launch with the lanes of a batch serialised (each launch "
+                            "alone on the GPU, same kernels and inputs, right after the timed region); in_pipeline: the "
+                            "same events while lanes and batches overlap, so a launch's duration includes the time it "
+                            "shares the SMs with other kernels; share_of_step = summed in-pipeline launch time / wall time",
                     "peak_source": "measured in this run by hk_bench_imad_wide (MEASURED_PEAKS.json has no integer peak)"}
-        ms_ntt, n_ntt, elems = prof[2]
+        ms_ntt, n_ntt, elems = prof_alone[2]
+        ms_ntt_p, n_ntt_p, elems_p = prof[2]
         roof_ntt = None
         if n_ntt:
             gbs = elems * 64 / (ms_ntt * 1e-3) / 1e9
             roof_ntt = {"kernel": "k_ntt_pass", "bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s",
                         "frac": gbs / hbm_gbs, "traffic": None, "launches": n_ntt, "avg_launch_ms": ms_ntt / n_ntt,
-                        "share_of_step": ms_ntt / ms_dev, "peak_source": f"{hbm_src} (MEASURED_PEAKS.json hbm_gbs)",
-                        "note": "64 B per element per pass (read + write once)"}
+                        "share_of_step": (ms_ntt_p / ms_prof) if ms_prof else None,
+                        "peak_source": f"{hbm_src} (MEASURED_PEAKS.json hbm_gbs)",
+                        "note": "64 B per element per pass (read + write once); launches timed alone (lanes serialised). "
+                                "A pass is multiplier-bound, not HBM-bound (136 wide MACs per butterfly): see extras for "
+                                "the IMAD fraction"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -487,7 +546,7 @@ def main():
             "gpu_launches": launches, "roofline": roof, "roofline_ntt": roof_ntt, "cpu_baseline": cpu, "extras": extras,
             "verified_vs_trapdoor": verified,
         }
-        print(json.dumps(line))
+        emit(line)
     for c_ in all_ctxs:
         c_.close()
     ctx.close()

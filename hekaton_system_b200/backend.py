@@ -394,8 +394,10 @@ class Context:
                                       out.ctypes.data, n))
         return out
 
-    def profile(self, on=True):
-        self._ck(self.lib.hk_profile_enable(self.h, 1 if on else 0))
+    def profile(self, on=True, serial=False):
+        """serial=True additionally maps every lane of commit/prove to the context stream so that each
+        launch is timed alone (hk_profile_enable mode 2)."""
+        self._ck(self.lib.hk_profile_enable(self.h, (2 if serial else 1) if on else 0))
 
     def profile_reset(self):
         self._ck(self.lib.hk_profile_reset(self.h))

@@ -789,6 +789,7 @@ HK_EXPORT int32_t hk_profile_enable(hk_ctx* ctx, int32_t on) {
     return guarded(ctx, [&] {
         HK_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->prof_on = on != 0;
+        ctx->serial_lanes = on == 2;
     });
 }
 HK_EXPORT int32_t hk_profile_reset(hk_ctx* ctx) {

@@ -195,8 +195,11 @@ struct hk_ctx {
     hk::MsmWs mws[LANES];              // one MSM scratch per lane
     hk::DevBuf ws_out;
     hk::DevBuf ws_ntt_tmp, ws_qap[4], ws_io[6], ws_z, ws_misc;
-    cudaStream_t lane_stream(int lane) const { return lane > 0 && lane < LANES ? lane_ctl[lane] : stream; }
-    cudaStream_t bulk_stream(int lane) const { return lane > 0 && lane < LANES ? lane_bulk[lane] : stream; }
+    // serial_lanes (hk_profile_enable(ctx, 2)): every lane maps to the caller's stream, so kernels run one
+    // at a time and the profiling events bracket each kernel alone (roofline measurements)
+    bool serial_lanes = false;
+    cudaStream_t lane_stream(int lane) const { return !serial_lanes && lane > 0 && lane < LANES ? lane_ctl[lane] : stream; }
+    cudaStream_t bulk_stream(int lane) const { return !serial_lanes && lane > 0 && lane < LANES ? lane_bulk[lane] : stream; }
     // stream used by the NTT / QAP kernels (normally the main stream; prove_run points it at the H lane)
     cudaStream_t qap_stream = nullptr;
     cudaStream_t qstream() const { return qap_stream ? qap_stream : stream; }

@@ -390,7 +390,7 @@ void commit_run(hk_ctx* ctx, PkDev& pk, uint32_t stage, size_t K, const uint64_t
     const size_t nw = pk.stage_start[stage + 1] - pk.stage_start[stage];
     // a commitment is a small latency-bound MSM: run it on a prioritised lane so that, when other
     // contexts keep the GPU busy (proofs of the previous batch), its kernels are served promptly
-    cudaStream_t ls = ctx->lane_ctl[1];
+    cudaStream_t ls = ctx->lane_stream(1);
     HK_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
     HK_CUDA(cudaStreamWaitEvent(ls, ctx->ev_fork, 0));
     Fr* sc = ctx->ws_io[0].as<Fr>(K * (nw + 1));
@@ -438,27 +438,27 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     // which runs on the lane's control stream meanwhile), and L' last (shortest tail left exposed).
     enum { LA = 1, LB1 = 2, LB2 = 3, LH = 4, LL = 5 };
     HK_CUDA(cudaEventRecord(ctx->ev_fork, st));
-    for (int ln = 1; ln < hk_ctx::LANES; ln++) HK_CUDA(cudaStreamWaitEvent(ctx->lane_ctl[ln], ctx->ev_fork, 0));
+    for (int ln = 1; ln < hk_ctx::LANES; ln++) HK_CUDA(cudaStreamWaitEvent(ctx->lane_stream(ln), ctx->ev_fork, 0));
     msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, Sr, K, false, jac + 0, 0, LA);
-    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LA], ctx->lane_ctl[LA]));
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LA], ctx->lane_stream(LA)));
     msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, Ss, K, false, jac + K, 0, LB1);
     // s*A, r*B1 and A's normalisation, on B1's control stream once A is there too
     XYZZ<Fq>* sab = ctx->ws_io[2].as<XYZZ<Fq>>(2 * K);
-    HK_CUDA(cudaStreamWaitEvent(ctx->lane_ctl[LB1], ctx->ev_lane_done[LA], 0));
-    k_prove_finish_ab<Curve><<<Ku, 64, 0, ctx->lane_ctl[LB1]>>>(jac, jac + K, r, s, sab,
+    HK_CUDA(cudaStreamWaitEvent(ctx->lane_stream(LB1), ctx->ev_lane_done[LA], 0));
+    k_prove_finish_ab<Curve><<<Ku, 64, 0, ctx->lane_stream(LB1)>>>(jac, jac + K, r, s, sab,
                                                                  reinterpret_cast<Affine<Fq>*>(d_outA), d_inf);
     HK_LAUNCH_CHECK(ctx);
-    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LB1], ctx->lane_ctl[LB1]));
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LB1], ctx->lane_stream(LB1)));
     // the G2 MSM + B2's normalisation
     msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, Ss, K, false, jacB2, 0, LB2);
-    k_prove_finish_b2<Curve><<<Ku, 32, 0, ctx->lane_ctl[LB2]>>>(jacB2, reinterpret_cast<Affine<Fq2>*>(d_outB), d_inf);
+    k_prove_finish_b2<Curve><<<Ku, 32, 0, ctx->lane_stream(LB2)>>>(jacB2, reinterpret_cast<Affine<Fq2>*>(d_outB), d_inf);
     HK_LAUNCH_CHECK(ctx);
-    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LB2], ctx->lane_ctl[LB2]));
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LB2], ctx->lane_stream(LB2)));
     // witness map, then the H MSM (they need only z)
     uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N * K);
     uint64_t* h = ctx->ws_qap[1].as<uint64_t>(4 * N * K);
     ntt_domain<Curve>(ctx, log_n);                 // build (and synchronise) the tables before switching streams
-    ctx->qap_stream = ctx->lane_ctl[LH];
+    ctx->qap_stream = ctx->lane_stream(LH);
     try {
         r1cs_evals<Curve>(ctx, *pk.r1cs, d_z_v, abc, K);
         qap_h_from_evals<Curve>(ctx, log_n, abc, h, K);
@@ -469,20 +469,24 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     ctx->qap_stream = nullptr;
     msm_run<Curve, 1>(ctx, msm_view(*pk.h_g), 0, N - 1, reinterpret_cast<const Scalar256*>(h), K, true, jac + 3 * K,
                       /*sc_stride=*/N, LH);
-    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LH], ctx->lane_ctl[LH]));
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LH], ctx->lane_stream(LH)));
     // L'
     const size_t nl = pk.stage_start[ns] - pk.stage_start[ns - 1];
     Fr* Ls = ctx->ws_io[1].as<Fr>(K * (nl + ns));
-    k_build_l_scalars<Fr><<<dim3(ceil_div(nl + ns, 256), Ku), 256, 0, ctx->lane_ctl[LL]>>>(
+    k_build_l_scalars<Fr><<<dim3(ceil_div(nl + ns, 256), Ku), 256, 0, ctx->lane_stream(LL)>>>(
         z, m, l + pk.stage_start[ns - 1], nl, r, s, reinterpret_cast<const Fr*>(d_kappas), ns - 1, Ls);
     HK_LAUNCH_CHECK(ctx);
     msm_run<Curve, 1>(ctx, msm_view(*pk.ck_ext[ns - 1]), 0, nl + ns, reinterpret_cast<const Scalar256*>(Ls), K, true,
                       jac + 2 * K, 0, LL);
-    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LL], ctx->lane_ctl[LL]));
-    for (int ln : {LB1, LB2, LH, LL}) HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_lane_done[ln], 0));
-    k_prove_finish_c<Curve><<<Ku, 32, 0, st>>>(sab, jac + 2 * K, jac + 3 * K, reinterpret_cast<Affine<Fq>*>(d_outC), d_inf,
-                                               Ku);
+    // C = s*A + r*B1 + L' + H on L''s control stream (the caller's stream usually has the lowest priority
+    // and would be served only after every queued accumulation of the batches behind this one)
+    cudaStream_t fin = ctx->lane_stream(LL);
+    for (int ln : {LB1, LH}) HK_CUDA(cudaStreamWaitEvent(fin, ctx->ev_lane_done[ln], 0));
+    k_prove_finish_c<Curve><<<Ku, 32, 0, fin>>>(sab, jac + 2 * K, jac + 3 * K, reinterpret_cast<Affine<Fq>*>(d_outC), d_inf,
+                                                Ku);
     HK_LAUNCH_CHECK(ctx);
+    HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LL], fin));
+    for (int ln : {LB2, LL}) HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_lane_done[ln], 0));
 }
 template void prove_run<Bls12381>(hk_ctx*, PkDev&, size_t, const uint64_t*, const uint64_t*, const uint64_t*,
                                   const uint64_t*, void*, void*, void*, uint8_t*);

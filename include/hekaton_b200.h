@@ -221,7 +221,11 @@ int32_t hk_bench_field_mul(hk_ctx* ctx, uint32_t field, uint32_t threads, uint32
  * by CUDA events on the context stream and their work counts are recorded:
  *   HK_PROF_MSM_ACCUM_G1 / _G2  units = bucket-accumulation point additions
  *   HK_PROF_NTT_PASS            units = field elements read+written by a pass
- * hk_profile_read synchronises the stream and returns totals since the last reset. */
+ * hk_profile_read synchronises the stream and returns totals since the last reset.
+ * on = 1: time the kernels as they run (several lanes of a proof batch overlap, so a launch's duration
+ *         includes the time it shares the GPU with others);
+ * on = 2: additionally serialise the lanes of hk_commit* / hk_prove* onto the context stream, so that every
+ *         launch is timed alone (same kernels, same inputs; the batch itself runs slower). */
 enum { HK_PROF_MSM_ACCUM_G1 = 0, HK_PROF_MSM_ACCUM_G2 = 1, HK_PROF_NTT_PASS = 2, HK_PROF_COUNT = 3 };
 int32_t hk_profile_enable(hk_ctx* ctx, int32_t on);
 int32_t hk_profile_reset(hk_ctx* ctx);
