@@ -16,7 +16,7 @@ SCALAR_BIGINT, SCALAR_MONT = 0, 1
 NTT_FORWARD, NTT_INVERSE = 0, 1
 DOMAIN_PLAIN, DOMAIN_COSET = 0, 1
 FIELD_FR, FIELD_FQ, FIELD_FQ2 = 0, 1, 2
-FOP_MUL, FOP_ADD, FOP_SUB, FOP_INV, FOP_TO_MONT, FOP_FROM_MONT, FOP_INV_GCD = range(7)
+FOP_MUL, FOP_ADD, FOP_SUB, FOP_INV, FOP_TO_MONT, FOP_FROM_MONT, FOP_INV_GCD, FOP_SQR = range(8)
 
 ERRORS = {0: "HK_OK", -1: "HK_ERR_INVALID", -2: "HK_ERR_CUDA", -3: "HK_ERR_NOMEM", -4: "HK_ERR_LENGTH",
           -5: "HK_ERR_HANDLE", -6: "HK_ERR_UNSUPPORTED", -7: "HK_ERR_NO_DEVICE"}

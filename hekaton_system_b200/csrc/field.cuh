@@ -17,6 +17,7 @@ namespace hk {
         static constexpr int N64 = NAME##_params::N64;                                        \
         static constexpr int BITS = NAME##_params::BITS;                                      \
         __device__ __forceinline__ static void mul(raw_t& r, const raw_t& a, const raw_t& b) { NAME##_mul(r, a, b); } \
+        __device__ __forceinline__ static void sqr(raw_t& r, const raw_t& a) { NAME##_sqr(r, a); }            \
         __device__ __forceinline__ static void add(raw_t& r, const raw_t& a, const raw_t& b) { NAME##_add(r, a, b); } \
         __device__ __forceinline__ static void sub(raw_t& r, const raw_t& a, const raw_t& b) { NAME##_sub(r, a, b); } \
         __device__ __forceinline__ static uint64_t mod(int i) { return NAME##_MOD[i]; }       \
@@ -36,6 +37,14 @@ template <class Tag>
 __device__ __noinline__ typename Tag::raw_t fp_mul_call(typename Tag::raw_t a, typename Tag::raw_t b) {
     typename Tag::raw_t r;
     Tag::mul(r, a, b);
+    return r;
+}
+
+// Dedicated squaring (N(N+1)/2 + N^2 + N wide multiplies instead of 2N^2 + N), same call convention.
+template <class Tag>
+__device__ __noinline__ typename Tag::raw_t fp_sqr_call(typename Tag::raw_t a) {
+    typename Tag::raw_t r;
+    Tag::sqr(r, a);
     return r;
 }
 
@@ -80,9 +89,9 @@ struct Fp {
     __device__ __forceinline__ Fp operator+(const Fp& b) const { Fp o; Tag::add(o.r, r, b.r); return o; }
     __device__ __forceinline__ Fp operator-(const Fp& b) const { Fp o; Tag::sub(o.r, r, b.r); return o; }
 #ifdef HK_MUL_CALL
-    __device__ __forceinline__ Fp sqr() const { Fp o; o.r = fp_mul_call<Tag>(r, r); return o; }
+    __device__ __forceinline__ Fp sqr() const { Fp o; o.r = fp_sqr_call<Tag>(r); return o; }
 #else
-    __device__ __forceinline__ Fp sqr() const { Fp o; Tag::mul(o.r, r, r); return o; }
+    __device__ __forceinline__ Fp sqr() const { Fp o; Tag::sqr(o.r, r); return o; }
 #endif
     __device__ __forceinline__ Fp dbl() const { Fp o; Tag::add(o.r, r, r); return o; }
     __device__ __forceinline__ Fp neg() const { Fp z = zero(); Fp o; Tag::sub(o.r, z.r, r); return o; }

@@ -75,7 +75,8 @@ enum {
 /* Field ids for the element-wise test entry point. */
 enum { HK_FIELD_FR = 0, HK_FIELD_FQ = 1, HK_FIELD_FQ2 = 2 };
 enum { HK_FOP_MUL = 0, HK_FOP_ADD = 1, HK_FOP_SUB = 2, HK_FOP_INV = 3, HK_FOP_TO_MONT = 4, HK_FOP_FROM_MONT = 5,
-       HK_FOP_INV_GCD = 6 /* binary-GCD inverse (the one affine normalisation uses) */ };
+       HK_FOP_INV_GCD = 6 /* binary-GCD inverse (the one affine normalisation uses) */,
+       HK_FOP_SQR = 7 /* dedicated Montgomery squaring (falls back to a*a where the field has no spare bits) */ };
 
 /* ---- context ---------------------------------------------------------------------- */
 /* `stream`: a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create one. */

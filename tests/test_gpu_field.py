@@ -43,7 +43,11 @@ def test_prime_field_ops(ctx, field):
     am = [x * R % mod for x in a[:200]]
     got = codec.limbs_to_ints(ctx.field_op(field, B.FOP_INV, codec.ints_to_limbs(am, L)))
     assert got == [(pow(x, -1, mod) * R % mod) if x % mod else 0 for x in a[:200]]
-    # binary-GCD inverse (ALU-pipe variant used by the batch-affine rounds): same values
+    # dedicated squaring (generated separately from the multiply): a^2 R^-1, random and top-of-range values
+    sq = a[:400] + [mod - 1 - k for k in range(40)] + [(mod - 1) // 2, 1 << (mod.bit_length() - 1)]
+    got = codec.limbs_to_ints(ctx.field_op(field, B.FOP_SQR, codec.ints_to_limbs(sq, L)))
+    assert got == [x * x * pow(R, -1, mod) % mod for x in sq]
+    # binary-GCD inverse (ALU-pipe variant used by the affine normalisations): same values
     got = codec.limbs_to_ints(ctx.field_op(field, B.FOP_INV_GCD, codec.ints_to_limbs(am, L)))
     assert got == [(pow(x, -1, mod) * R % mod) if x % mod else 0 for x in a[:200]]
 

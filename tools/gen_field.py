@@ -116,10 +116,19 @@ class Prog:
                 R[dst] = val(srcs[0]) if R[srcs[2]] else val(srcs[1])
             elif op == "and.b64":
                 R[dst] = val(srcs[0]) & val(srcs[1])
+            elif op == "add.u32":
+                R[dst] = (val(srcs[0]) + val(srcs[1])) & M32
+            elif op == "shl.b32":
+                R[dst] = (val(srcs[0]) << val(srcs[1])) & M32
+            elif op == "shf.l.wrap.b32":      # upper 32 bits of (hi:lo) << n
+                lo_, hi_, n_ = val(srcs[0]), val(srcs[1]), val(srcs[2]) & 31
+                R[dst] = (((hi_ << 32) | lo_) << n_ >> 32) & M32
             elif op == "assert_nc":
                 assert cf == 0, "dropped a non-zero carry"
             elif op == "assert_lo0":
                 assert val(srcs[0]) & M32 == 0
+            elif op == "assert_hi0":
+                assert val(srcs[0]) == 0, "non-zero bits above the result"
             else:
                 raise ValueError(op)
         return R
@@ -142,7 +151,7 @@ class Prog:
         if self.preds:
             lines.append(".reg .pred " + ", ".join(self.preds) + ";")
         for op, dst, srcs in self.ins:
-            if op in ("assert_nc", "assert_lo0"):
+            if op in ("assert_nc", "assert_lo0", "assert_hi0"):
                 continue
             if op == "unpack":
                 lines.append(f"mov.b64 {{{o(dst[0])}, {o(dst[1])}}}, {o(srcs[0])};")
@@ -172,6 +181,8 @@ class FieldGen:
         self.m32 = (-pow(p, -1, 1 << 32)) % (1 << 32)
         self.pl = limbs32(p, self.N)
         self.p64 = lanes64(p, self.N2)
+        # dedicated squaring needs 2a + p < 2^(32N) for every a < p (see gen_sqr)
+        self.has_sqr = 3 * p < (1 << (32 * self.N))
 
     # -- shared tail: r (N2 lanes, < 2p) -> r mod p into output names
     def _final_sub(self, P, lanes, outs):
@@ -273,6 +284,123 @@ class FieldGen:
         P.emit("assert_nc", None)
         self._final_sub(P, res, outs)
         return P, outs, ain + bin_
+
+    def gen_sqr(self):
+        """Dedicated Montgomery squaring: every off-diagonal product a_i*a_k (i < k) is taken once against
+        the doubled operand, N(N+1)/2 + N^2 + N wide multiplies instead of 2N^2 + N.
+        Row i (interleaved with its reduction row exactly as in gen_mul) adds
+            a_i * a_i                      at lane 2i
+            a_i * E_k,  k > i              at lane i + k,   E = 2 * (a with limbs <= i cleared):
+                E_(i+1) = (a_(i+1) << 1) mod 2^32,   E_k = (a_k << 1 | a_(k-1) >> 31) for k >= i + 2
+        (2a < 2^(32N) needs one spare top bit; the carry invariants of gen_mul additionally need
+        2a + p < 2^(32N), i.e. TWO spare bits -- checked in __init__ via `self.has_sqr`).
+        Column i is complete before reduction row i: a pair (j, k), j < k, j + k = i was added in row j < i."""
+        N, N2 = self.N, self.N2
+        assert self.has_sqr
+        P = Prog()
+        outs = [f"r{k}" for k in range(N2)]
+        ain = [f"a{k}" for k in range(N2)]
+        a = []
+        for k in range(N2):
+            lo, hi = P.r32("al"), P.r32("ah")
+            P.emit("unpack", (lo, hi), ain[k])
+            a += [lo, hi]
+        D, Dn = {}, {}          # D[k] = (a_k << 1 | a_(k-1) >> 31), Dn[k] = a_k << 1
+        for k in range(1, N):
+            Dn[k] = P.r32("dn")
+            P.emit("shl.b32", Dn[k], a[k], 1)
+            D[k] = P.r32("d")
+            P.emit("shf.l.wrap.b32", D[k], a[k - 1], a[k], 1)
+        L = {}
+        x = None
+
+        def chain(cols, prods, carry_lane, first_addend=None):
+            carrying = False
+            for idx, (c, (u, v)) in enumerate(zip(cols, prods)):
+                t = P.r64("t")
+                if idx == 0 and first_addend is not None:
+                    x64 = P.r64("x")
+                    P.emit("pack", x64, first_addend, 0)
+                    P.emit("mad.wide.u32", t, u, v, x64)
+                else:
+                    P.emit("mul.wide.u32", t, u, v)
+                if c in L:
+                    P.emit("addc.cc.u64" if carrying else "add.cc.u64", L[c], L[c], t)
+                    carrying = True
+                else:
+                    if carrying:
+                        L[c] = P.r64("L")
+                        P.emit("addc.cc.u64", L[c], t, 0)
+                    else:
+                        L[c] = t
+            if carry_lane is None:
+                if carrying:
+                    P.emit("assert_nc", None)
+            elif carrying:
+                if carry_lane in L:
+                    P.emit("addc.u64", L[carry_lane], L[carry_lane], 0)
+                else:
+                    L[carry_lane] = P.r64("L")
+                    P.emit("addc.u64", L[carry_lane], 0, 0)
+
+        def carry_lane_for(i, js):
+            # the chain's last lane is i + js[-1]; a carry out of it lands two lanes up.  Lanes up to i + N - 1
+            # can be live in row i, so only a chain ending at i + N - 2 may carry (into lane i + N); one ending at
+            # lane i + N - 1 cannot, because the running total stays below 2^(32 (i + N + 1)) (see docstring).
+            return i + N if js[-1] == N - 2 else None
+
+        for i in range(N):
+            opnd = {i: a[i]}
+            for k in range(i + 1, N):
+                opnd[k] = Dn[k] if k == i + 1 else D[k]
+            same = [j for j in range(i, N) if (j - i) % 2 == 0]        # lanes 2i, 2i+2, ...: the family of lane i
+            other = [j for j in range(i + 1, N) if (j - i) % 2 == 1]
+            chain([i + j for j in same], [(a[i], opnd[j]) for j in same], carry_lane_for(i, same))
+            if other:
+                chain([i + j for j in other], [(a[i], opnd[j]) for j in other], carry_lane_for(i, other))
+            # column i = lo32(L[i]) + x  (x: high half of the lane retired by the previous row)
+            lo, hi = P.r32("lo"), P.r32("hi")
+            P.emit("unpack", (lo, hi), L[i])
+            m = P.r32("m")
+            if x is None:
+                P.emit("mul.lo.u32", m, lo, self.m32)
+            else:
+                sx = P.r32("sx")
+                P.emit("add.u32", sx, lo, x)
+                P.emit("mul.lo.u32", m, sx, self.m32)
+            ev = list(range(0, N, 2))
+            od = list(range(1, N, 2))
+            chain([i + j for j in ev], [(m, self.pl[j]) for j in ev], i + N, first_addend=x)
+            chain([i + j for j in od], [(m, self.pl[j]) for j in od], None)
+            P.emit("assert_lo0", None, L[i])
+            lo2, hi2 = P.r32("z"), P.r32("x")
+            P.emit("unpack", (lo2, hi2), L[i])
+            x = hi2
+            del L[i]
+        odd32 = {N: x}
+        for c in range(N + 1, 2 * N, 2):
+            if c in L:
+                lo, hi = P.r32("ol"), P.r32("oh")
+                P.emit("unpack", (lo, hi), L[c])
+                odd32[c] = lo
+                if c + 1 < 2 * N:
+                    odd32[c + 1] = hi
+                else:
+                    P.emit("assert_hi0", None, hi)
+        res = []
+        for k in range(N2):
+            c = N + 2 * k
+            o64 = P.r64("o")
+            P.emit("pack", o64, odd32.get(c, 0), odd32.get(c + 1, 0))
+            lane = L.get(c)
+            if lane is None:
+                lane = P.r64("L")
+                P.emit("mov.u64", lane, 0)
+            P.emit("add.cc.u64" if k == 0 else "addc.cc.u64", lane, lane, o64)
+            res.append(lane)
+        P.emit("assert_nc", None)
+        self._final_sub(P, res, outs)
+        return P, outs, ain
 
     def gen_add(self):
         N2 = self.N2
@@ -383,9 +511,17 @@ def emit_header(path):
         out.append(f"__device__ __constant__ const uint64_t {name}_R2[{n2}] = {c_array64(R * R % p, n2)};    // R^2 mod p\n")
         for cname, val, doc in extra_constants().get(name, []):
             out.append(f"__device__ __constant__ const uint64_t {name}_{cname}[{n2}] = {c_array64(val, n2)};   // {doc}\n")
-        for fname, gen in (("mul", fg.gen_mul), ("add", fg.gen_add), ("sub", fg.gen_sub)):
+        out.append(f"#define HK_HAS_SQR_{name} {1 if fg.has_sqr else 0}\n")
+        gens = [("mul", fg.gen_mul), ("add", fg.gen_add), ("sub", fg.gen_sub)]
+        if fg.has_sqr:
+            gens.append(("sqr", fg.gen_sqr))
+        for fname, gen in gens:
             P, outs, ins = gen()
             out.append(fg.cpp_fn(fname, P, outs, ins))
+        if not fg.has_sqr:
+            out.append(f"// no dedicated squaring: 3p >= 2^{32 * fg.N} (the carry invariants need two spare bits)\n"
+                       f"__device__ __forceinline__ void {name}_sqr({name}_t& r, const {name}_t& a) "
+                       f"{{ {name}_mul(r, a, a); }}\n")
         out.append("\n")
     out.append("}  // namespace hk\n")
     with open(path, "w") as f:
@@ -400,6 +536,8 @@ def selftest(iters=200, seed=1):
         R = fg.R
         Rinv = pow(R, -1, p)
         progs = {k: g() for k, g in (("mul", fg.gen_mul), ("add", fg.gen_add), ("sub", fg.gen_sub))}
+        if fg.has_sqr:
+            progs["sqr"] = fg.gen_sqr()
         edge = [0, 1, 2, p - 1, p - 2, R % p, (R * R) % p, (p - 1) // 2, (1 << (p.bit_length() - 1)),
                 (1 << (p.bit_length() - 1)) - 1, p - (1 << 64), (1 << 64) - 1, (1 << 32) - 1]
         edge = [e % p for e in edge]
@@ -415,6 +553,18 @@ def selftest(iters=200, seed=1):
                 Rr = P.run(env)
                 got = sum(Rr[o] << (64 * k) for k, o in enumerate(outs))
                 assert got == ref, (name, op, hex(x), hex(y), hex(got), hex(ref))
+        if fg.has_sqr:
+            P, outs, ins = progs["sqr"]
+            top = [p - 1, p - 2, (p - 1) // 2, (1 << (p.bit_length() - 1)), (1 << (p.bit_length() - 1)) - 1,
+                   p - (1 << 64), p - (1 << 32) - 1, int("f" * (p.bit_length() // 4 - 1), 16) % p]
+            for x in edge + top + [rng.randrange(p) for _ in range(3 * iters)] + \
+                    [p - 1 - rng.randrange(1 << 40) for _ in range(iters)]:
+                env = {f"a{k}": lanes64(x, n2)[k] for k in range(n2)}
+                Rr = P.run(env)
+                got = sum(Rr[o] << (64 * k) for k, o in enumerate(outs))
+                assert got == x * x * Rinv % p, (name, "sqr", hex(x), hex(got))
+            nsq = sum(1 for op, _, _ in P.ins if op in ("mul.wide.u32", "mad.wide.u32"))
+            print(f"{name}: sqr ok ({nsq} wide multiplies)")
         nmul = sum(1 for op, _, _ in progs["mul"][0].ins if op in ("mul.wide.u32", "mad.wide.u32"))
         print(f"{name}: ok  ({len(cases)} cases; mul = {nmul} wide multiplies, "
               f"{len(progs['mul'][0].ins)} PTX instructions)")
