@@ -55,7 +55,7 @@ static constexpr uint32_t NTT_TMAX = 11;   // tile = 2^11 elements = 64 KiB of s
 static constexpr uint32_t NTT_QMAX = 2;
 static constexpr uint32_t NTT_TPB = 256;   // one radix-8 group per thread and round on a full tile
 
-enum : uint32_t { NTT_PERM_IN = 1, NTT_PERM_OUT = 2 };
+enum : uint32_t { NTT_PERM_IN = 1, NTT_PERM_OUT = 2, NTT_TOP_PASS = 4 };
 
 struct NttDomain {
     uint32_t log_n = 0;
@@ -75,14 +75,23 @@ struct NttPass {
     uint32_t s0, k, q, T;
 };
 
-inline std::vector<NttPass> ntt_plan(uint32_t log_n) {
+// `perm`: the transform carries a bit reversal on its L = 0 pass (hk_ntt: natural order in and out).  A tile of
+// 2^11 CONSECUTIVE elements then gathers / scatters single 32-byte elements 2^(log_n - 11) apart, which
+// over-fetches DRAM 2-4x once the vector outgrows L2.  So for log_n >= NTT_TOP_MIN that pass takes only 9
+// stages and its tile carries the TOP two index bits as passengers: after the bit reversal they are the two
+// lowest address bits, i.e. every access is a 128-byte run.  Same number of passes for log_n >= 21.
+static constexpr uint32_t NTT_TOP_MIN = 21;
+static constexpr uint32_t NTT_TOP_BITS = 2;
+
+inline std::vector<NttPass> ntt_plan(uint32_t log_n, bool perm = false) {
     std::vector<NttPass> p;
     if (log_n == 0) return p;
     if (log_n <= NTT_TMAX) {
         p.push_back({0, log_n, 0, log_n});
         return p;
     }
-    uint32_t last = NTT_TMAX;
+    const bool top = perm && log_n >= NTT_TOP_MIN;
+    uint32_t last = top ? NTT_TMAX - NTT_TOP_BITS : NTT_TMAX;
     uint32_t rest = log_n - last;
     uint32_t per = NTT_TMAX - NTT_QMAX;
     uint32_t np = (rest + per - 1) / per;
@@ -126,10 +135,12 @@ __device__ __forceinline__ void sm_store(uint4* lo, uint4* hi, uint32_t e, const
 // tile element e -> global index (see k_ntt_pass)
 struct NttTileMap {
     uint32_t q, k, L, hs_bits, block;
+    uint32_t top_shift;          // != 0: L = q = 0 pass whose hs_bits passenger bits are the TOP index bits
     __device__ __forceinline__ uint32_t operator()(uint32_t e) const {
         uint32_t lq = e & ((1u << q) - 1);
         uint32_t m = (e >> q) & ((1u << k) - 1);
         uint32_t hsub = e >> (q + k);
+        if (top_shift) return (hsub << top_shift) | (block << k) | m;
         uint32_t outer = (block << hs_bits) | hsub;
         uint32_t lhi = outer & ((1u << (L - q)) - 1);
         uint32_t H = outer >> (L - q);
@@ -200,9 +211,17 @@ k_ntt_pass(const Fr* in_all, Fr* out_all, const Fr* __restrict__ tw, uint32_t lo
     Fr* out = out_all + (size_t)blockIdx.y * N;
     const uint32_t L = log_n - s0 - k;
     const uint32_t tile = 1u << T;
-    const NttTileMap gidx{q, k, L, T - k - q, blockIdx.x};
+    const uint32_t hs_bits = T - k - q;
+    const bool top = (flags & NTT_TOP_PASS) != 0;
+    const NttTileMap gidx{q, k, L, hs_bits, blockIdx.x, top ? log_n - hs_bits : 0u};
 
-    for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
+    // top-passenger tiles enumerate the passenger bits fastest, so that consecutive threads touch the
+    // consecutive (bit-reversed) addresses of one 128-byte run
+    auto tile_elem = [&](uint32_t ee) -> uint32_t {
+        return top ? (((ee & ((1u << hs_bits) - 1)) << k) | (ee >> hs_bits)) : ee;
+    };
+    for (uint32_t ee = threadIdx.x; ee < tile; ee += blockDim.x) {
+        const uint32_t e = tile_elem(ee);
         uint32_t i = gidx(e);
         uint32_t src = (flags & NTT_PERM_IN) ? bitrev(i, log_n) : i;
         Fr x = in[src];
@@ -226,7 +245,8 @@ k_ntt_pass(const Fr* in_all, Fr* out_all, const Fr* __restrict__ tw, uint32_t lo
 
     Fr pc;
     if (post_const) pc = *post_const;
-    for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
+    for (uint32_t ee = threadIdx.x; ee < tile; ee += blockDim.x) {
+        const uint32_t e = tile_elem(ee);
         uint32_t i = gidx(e);
         uint32_t dst = (flags & NTT_PERM_OUT) ? bitrev(i, log_n) : i;
         Fr x = sm_load<Fr>(slo, shi, e);
@@ -372,7 +392,9 @@ void ntt_passes(hk_ctx* ctx, const NttDomain& d, bool dit, bool inverse_root, co
                 const typename Curve::Fr* post_const, bool src_clobber_ok = false) {
     using Fr = typename Curve::Fr;
     const uint32_t log_n = d.log_n;
-    auto plan = ntt_plan(log_n);
+    // the bit reversal sits on the L = 0 pass only for DIT + perm_in (first pass) and DIF + perm_out (last pass)
+    const bool top_pass = ((dit && perm_in) || (!dit && perm_out)) && log_n >= NTT_TOP_MIN && log_n > NTT_TMAX;
+    auto plan = ntt_plan(log_n, top_pass);
     const Fr* tw = reinterpret_cast<const Fr*>(inverse_root ? d.tw_inv : d.tw_fwd);
     const size_t np = plan.size();
     if (dit) {
@@ -391,7 +413,8 @@ void ntt_passes(hk_ctx* ctx, const NttDomain& d, bool dit, bool inverse_root, co
         uint32_t flags = 0;
         if (first && perm_in) flags |= NTT_PERM_IN;
         if (last && perm_out) flags |= NTT_PERM_OUT;
-        const bool oop = flags != 0;
+        if (top_pass && ps.s0 + ps.k == log_n) flags |= NTT_TOP_PASS;     // the L = 0 pass
+        const bool oop = (flags & (NTT_PERM_IN | NTT_PERM_OUT)) != 0;
         Fr* to;
         if (last) {
             to = dst;

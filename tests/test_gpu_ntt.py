@@ -51,7 +51,7 @@ def test_ntt_batch_and_device_pointer(ctx):
     assert codec.from_mont(t.cpu().numpy().view(np.uint64), cv.r) == dom.fft(xs[0])
 
 
-@pytest.mark.parametrize("log_n", [16, 20, 22])
+@pytest.mark.parametrize("log_n", [16, 20, 21, 22, 23])
 def test_ntt_large_properties(ctx, log_n):
     """Round trip, linearity and a single-coefficient known answer at sizes the O(N log N) oracle
     does not reach in seconds."""
@@ -85,6 +85,34 @@ def test_qap_h_matches_oracle(ctx, log_n):
     ref = poly.h_from_evals(cv.name, dom, a, b, c)
     h = ctx.qap_h(codec.to_mont(a, cv.r, 4), codec.to_mont(b, cv.r, 4), codec.to_mont(c, cv.r, 4), log_n)
     assert codec.from_mont(h, cv.r) == ref
+
+
+@pytest.mark.parametrize("log_n", [13, 21])
+def test_qap_h_equals_composition_of_transforms(ctx, log_n):
+    """hk_qap_h (DIF -> DIT -> pointwise -> DIF pipeline that never materialises a bit reversal; at
+    log_n >= 21 its last pass scatters through top-passenger tiles) against the same h assembled from
+    standalone hk_ntt calls (DIT with bit-reversed loads) and element-wise field ops: two disjoint kernel
+    paths.  log_n = 21 is the VM shape's domain (BASELINE config 5)."""
+    from hekaton_system_b200 import backend as B
+    cv = ctx.curve
+    n = 1 << log_n
+    rng = np.random.default_rng(log_n)
+    a, b, c = (rng.integers(0, 1 << 60, size=(n, 4), dtype=np.uint64) for _ in range(3))   # Montgomery residues < r
+    h = ctx.qap_h(a.copy(), b.copy(), c.copy(), log_n)
+    ev = []
+    for x in (a, b, c):
+        y = x.copy()
+        ctx.ntt(y, log_n, inverse=True)
+        ctx.ntt(y, log_n, coset=True)
+        ev.append(y)
+    ab = ctx.field_op(B.FIELD_FR, B.FOP_MUL, ev[0], ev[1])
+    num = ctx.field_op(B.FIELD_FR, B.FOP_SUB, ab, ev[2])
+    g = cv.fr_generator
+    zinv = pow(pow(g, n, cv.r) - 1, -1, cv.r)
+    zm = np.repeat(codec.to_mont([zinv], cv.r, 4), n, axis=0)
+    q = ctx.field_op(B.FIELD_FR, B.FOP_MUL, num, zm)
+    ctx.ntt(q, log_n, inverse=True, coset=True)
+    assert np.array_equal(q, h)
 
 
 @pytest.mark.parametrize("ncons", [3, 50, 700])
