@@ -74,6 +74,8 @@ def load_library(path=None):
         "hk_msm_g1_checked": [vp, u64, sz, sz, u64p, sz, u32, u32, vp],
         "hk_msm_g1_batch": [vp, u64, sz, u64p, sz, sz, u32, u32, vp],
         "hk_msm_g2_batch": [vp, u64, sz, u64p, sz, sz, u32, u32, vp],
+        "hk_scalar_mul_g1": [vp, vp, u8p, u64p, sz, u32, u32, vp, u8p],
+        "hk_scalar_mul_g2": [vp, vp, u8p, u64p, sz, u32, u32, vp, u8p],
         "hk_g1_into_affine": [vp, vp, sz, vp, u8p],
         "hk_g2_into_affine": [vp, vp, sz, vp, u8p],
         "hk_ntt": [vp, u64p, u32, u32, u32, u32],
@@ -258,6 +260,22 @@ class Context:
         fn = self.lib.hk_g1_into_affine if group == 1 else self.lib.hk_g2_into_affine
         self._ck(fn(self.h, jac.ctypes.data, n, out.ctypes.data, inf.ctypes.data))
         return out, inf
+
+    def scalar_mul(self, group, points, scalars, inf=None, repr_=SCALAR_BIGINT):
+        """out[i] = scalars[i] * points[i] (pairing_ops.rs:32-39 `scalar_pairing`): host arrays
+        points (n, 2L | 4L) Montgomery, scalars (n, 4) -> (affine points, infinity flags)."""
+        points = np.ascontiguousarray(points, dtype=np.uint64)
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        n = scalars.shape[0]
+        assert points.shape[0] == n
+        if inf is not None:
+            inf = np.ascontiguousarray(inf, dtype=np.uint8)
+        out = np.zeros_like(points)
+        oinf = np.zeros(n, dtype=np.uint8)
+        fn = self.lib.hk_scalar_mul_g1 if group == 1 else self.lib.hk_scalar_mul_g2
+        self._ck(fn(self.h, points.ctypes.data, _ptr(inf), scalars.ctypes.data, n, repr_, HK_HOST, out.ctypes.data,
+                    oinf.ctypes.data))
+        return out, oinf
 
     # ---- ntt / qap ----
     def ntt(self, data, log_n, inverse=False, coset=False, K=1):

@@ -469,6 +469,47 @@ HK_EXPORT int32_t hk_bases_from_scalars_g2(hk_ctx* ctx, const void* gen, const u
     return guarded(ctx, [&] { bases_from_scalars(ctx, 2, gen, scalars, n, repr, memspace, handle); });
 }
 
+// element-wise scalar multiplication (host or device buffers in `memspace`)
+static void scalar_mul_entry(hk_ctx* ctx, int group, const void* pts, const uint8_t* inf, const uint64_t* scalars, size_t n,
+                             uint32_t repr, uint32_t memspace, void* out_xy, uint8_t* inf_out) {
+    HK_REQUIRE(n == 0 || (pts && scalars && out_xy), HK_ERR_INVALID, "NULL argument");
+    HK_REQUIRE(repr == HK_SCALAR_BIGINT || repr == HK_SCALAR_MONT, HK_ERR_INVALID, "bad scalar representation");
+    if (n == 0) return;
+    const size_t pb = point_bytes(ctx, group);
+    const bool mont = repr == HK_SCALAR_MONT;
+    if (memspace == HK_DEVICE) {
+        by_curve(ctx,
+                 [&] {
+                     if (group == 1) scalar_mul_batch<Bls12381, 1>(ctx, pts, inf, (const Scalar256*)scalars, n, mont, out_xy, inf_out);
+                     else scalar_mul_batch<Bls12381, 2>(ctx, pts, inf, (const Scalar256*)scalars, n, mont, out_xy, inf_out);
+                 },
+                 [&] {
+                     if (group == 1) scalar_mul_batch<Bn254, 1>(ctx, pts, inf, (const Scalar256*)scalars, n, mont, out_xy, inf_out);
+                     else scalar_mul_batch<Bn254, 2>(ctx, pts, inf, (const Scalar256*)scalars, n, mont, out_xy, inf_out);
+                 });
+        return;
+    }
+    const void* d_p = to_device(ctx, ctx->ws_io[0], pts, pb * n, memspace);
+    const Scalar256* d_s = (const Scalar256*)to_device(ctx, ctx->ws_io[1], scalars, 32 * n, memspace);
+    const uint8_t* d_i = inf ? (const uint8_t*)to_device(ctx, ctx->ws_io[3], inf, n, memspace) : nullptr;
+    char* d_o = (char*)ctx->ws_io[2].ensure(pb * n + n + 64);
+    uint8_t* d_io = (uint8_t*)(d_o + pb * n);
+    scalar_mul_entry(ctx, group, d_p, d_i, (const uint64_t*)d_s, n, repr, HK_DEVICE, d_o, d_io);
+    HK_CUDA(cudaMemcpyAsync(out_xy, d_o, pb * n, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint8_t> tmp(n);
+    HK_CUDA(cudaMemcpyAsync(tmp.data(), d_io, n, cudaMemcpyDeviceToHost, ctx->stream));
+    HK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (inf_out) memcpy(inf_out, tmp.data(), n);
+}
+HK_EXPORT int32_t hk_scalar_mul_g1(hk_ctx* ctx, const void* points, const uint8_t* infinity, const uint64_t* scalars,
+                                   size_t n, uint32_t repr, uint32_t memspace, void* out_xy, uint8_t* inf_out) {
+    return guarded(ctx, [&] { scalar_mul_entry(ctx, 1, points, infinity, scalars, n, repr, memspace, out_xy, inf_out); });
+}
+HK_EXPORT int32_t hk_scalar_mul_g2(hk_ctx* ctx, const void* points, const uint8_t* infinity, const uint64_t* scalars,
+                                   size_t n, uint32_t repr, uint32_t memspace, void* out_xy, uint8_t* inf_out) {
+    return guarded(ctx, [&] { scalar_mul_entry(ctx, 2, points, infinity, scalars, n, repr, memspace, out_xy, inf_out); });
+}
+
 HK_EXPORT int32_t hk_msm_g1(hk_ctx* ctx, uint64_t bases, size_t off, const uint64_t* sc, size_t n, uint32_t repr,
                             uint32_t memspace, void* out) {
     return guarded(ctx, [&] { msm_entry(ctx, 1, bases, off, sc, n, 1, repr, memspace, out); });

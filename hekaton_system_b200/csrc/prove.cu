@@ -100,6 +100,33 @@ k_fixed_base_mul(const XYZZ<F>* __restrict__ tbl, const Scalar256* __restrict__ 
     out[i] = acc.to_affine();
 }
 
+// out[i] = scalars[i] * points[i], normalised -- the reference's `scalar_pairing`
+// (/root/reference/distributed-prover/src/pairing_ops.rs:32-39: per-element `*si * *ri`, then `normalize_batch`),
+// which the aggregator runs over the A / C / D / input vectors of all proofs (aggregation.rs:236-242,288-310).
+// `spread` threads per element (only the first of each group works): 32 = one warp per element, so the
+// data-dependent branches of the inversion and the digit tests do not serialise across elements.
+template <class F, class Fr>
+__global__ void __launch_bounds__(128)
+k_scalar_mul_batch(const Affine<F>* __restrict__ pts, const uint8_t* __restrict__ inf_in, const Scalar256* __restrict__ sc,
+                   int mont, Affine<F>* out, uint8_t* inf_out, size_t n, uint32_t spread) {
+    size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g % spread) return;
+    size_t i = g / spread;
+    if (i >= n) return;
+    uint64_t k[4] = {sc[i].v[0], sc[i].v[1], sc[i].v[2], sc[i].v[3]};
+    if (mont) {
+        Fr x;
+        for (int j = 0; j < 4; j++) x.r.v[j] = k[j];
+        x = x.from_mont();
+        for (int j = 0; j < 4; j++) k[j] = x.r.v[j];
+    }
+    Affine<F> p = pts[i];
+    XYZZ<F> acc = (inf_in && inf_in[i]) ? XYZZ<F>::inf() : XYZZ<F>::from_affine(p);
+    acc = scalar_mul<F>(acc, k);
+    out[i] = acc.to_affine();
+    if (inf_out) inf_out[i] = acc.is_inf() ? 1 : 0;
+}
+
 // ---- scalar staging ---------------------------------------------------------------------------
 // S = from_mont([ z[1..m-1], 1, 1, x ])  (m + 2 canonical scalars)
 // blockIdx.y = proof index p in the batch.  Writes both scalar vectors of the proof:
@@ -264,6 +291,23 @@ template void fixed_base_mul<Bls12381, 1>(hk_ctx*, const void*, const Scalar256*
 template void fixed_base_mul<Bls12381, 2>(hk_ctx*, const void*, const Scalar256*, size_t, bool, void*);
 template void fixed_base_mul<Bn254, 1>(hk_ctx*, const void*, const Scalar256*, size_t, bool, void*);
 template void fixed_base_mul<Bn254, 2>(hk_ctx*, const void*, const Scalar256*, size_t, bool, void*);
+
+template <class Curve, int GROUP>
+void scalar_mul_batch(hk_ctx* ctx, const void* d_pts, const uint8_t* d_inf, const Scalar256* d_scalars, size_t n, bool mont,
+                      void* d_out_affine, uint8_t* d_inf_out) {
+    using F = typename GroupFieldT<Curve, GROUP>::F;
+    using Fr = typename Curve::Fr;
+    if (n == 0) return;
+    const uint32_t spread = n <= 65536 ? 32u : 1u;
+    k_scalar_mul_batch<F, Fr><<<ceil_div(n * spread, 128), 128, 0, ctx->stream>>>(
+        reinterpret_cast<const Affine<F>*>(d_pts), d_inf, d_scalars, mont ? 1 : 0, reinterpret_cast<Affine<F>*>(d_out_affine),
+        d_inf_out, n, spread);
+    HK_LAUNCH_CHECK(ctx);
+}
+template void scalar_mul_batch<Bls12381, 1>(hk_ctx*, const void*, const uint8_t*, const Scalar256*, size_t, bool, void*, uint8_t*);
+template void scalar_mul_batch<Bls12381, 2>(hk_ctx*, const void*, const uint8_t*, const Scalar256*, size_t, bool, void*, uint8_t*);
+template void scalar_mul_batch<Bn254, 1>(hk_ctx*, const void*, const uint8_t*, const Scalar256*, size_t, bool, void*, uint8_t*);
+template void scalar_mul_batch<Bn254, 2>(hk_ctx*, const void*, const uint8_t*, const Scalar256*, size_t, bool, void*, uint8_t*);
 
 static std::shared_ptr<BaseSet> get_bases_sp(hk_ctx* ctx, uint64_t h, int group) {
     std::lock_guard<std::mutex> lk(ctx->sh->mu);

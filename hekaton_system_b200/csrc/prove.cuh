@@ -24,6 +24,10 @@ void jac_to_affine(hk_ctx* ctx, const void* d_jac, void* d_aff, uint8_t* d_inf, 
 template <class Curve, int GROUP>
 void fixed_base_mul(hk_ctx* ctx, const void* d_gen_affine, const Scalar256* d_scalars, size_t n, bool mont,
                     void* d_out_affine);
+// out[i] = scalars[i] * points[i] (affine in, affine out): pairing_ops.rs:32-39 `scalar_pairing`
+template <class Curve, int GROUP>
+void scalar_mul_batch(hk_ctx* ctx, const void* d_pts, const uint8_t* d_inf, const Scalar256* d_scalars, size_t n, bool mont,
+                      void* d_out_affine, uint8_t* d_inf_out);
 template <class Curve>
 std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d);
 template <class Curve>

@@ -25,6 +25,7 @@ SHAPES = {
     "big-merkle-small": (60_000, 1),    # config 1: 1 SHA2 iter, 1 portal  -> N = 2^16
     "big-merkle": (200_000, 8),         # config 3: 4 SHA2 iters, 8 portals -> N = 2^18
     "vm": (1_140_000, 776),             # config 5: 1024 cycles x 1114      -> N = 2^21
+    "vkd": (12_000, 4),                 # config 4: 32 Poseidon two-to-one hashes + exec-tree path -> N = 2^14
     "tiny": (500, 2),                   # tests / smoke
 }
 

@@ -137,6 +137,16 @@ int32_t hk_msm_g1_batch(hk_ctx* ctx, uint64_t bases, size_t base_offset, const u
 int32_t hk_msm_g2_batch(hk_ctx* ctx, uint64_t bases, size_t base_offset, const uint64_t* scalars, size_t n,
                         size_t K, uint32_t scalar_repr, uint32_t memspace, void* out_jacobian);
 
+/* Element-wise scalar multiplication out[i] = scalars[i] * points[i], normalised to affine: the reference's
+ * `scalar_pairing` (distributed-prover/src/pairing_ops.rs:32-39), which the aggregator applies to the A / C / D
+ * / prepared-input vectors of all proofs (aggregation.rs:236-242,288-310).  points: n affine points (Montgomery),
+ * infinity: n flags or NULL, scalars: n x 4 u64, out_xy: n affine points, inf_out: n bytes (may be NULL).
+ * Host or device pointers according to `memspace` (HK_HOST / HK_DEVICE). */
+int32_t hk_scalar_mul_g1(hk_ctx* ctx, const void* points, const uint8_t* infinity, const uint64_t* scalars, size_t n,
+                         uint32_t scalar_repr, uint32_t memspace, void* out_xy, uint8_t* inf_out);
+int32_t hk_scalar_mul_g2(hk_ctx* ctx, const void* points, const uint8_t* infinity, const uint64_t* scalars, size_t n,
+                         uint32_t scalar_repr, uint32_t memspace, void* out_xy, uint8_t* inf_out);
+
 /* Jacobian -> affine (CurveGroup::into_affine; prover.rs:152-154).  in: n*3 elements,
  * out: n*2 elements (Montgomery), inf_out: n bytes (may be NULL). Host pointers. */
 int32_t hk_g1_into_affine(hk_ctx* ctx, const void* jac, size_t n, void* out_xy, uint8_t* inf_out);

@@ -212,3 +212,28 @@ def test_msm_full_size_exact(ctx, group, log_n):
     e = sum(a * b for a, b in zip(ki, si)) % cv.r
     assert dec(aff, cv, inf)[0] == G.mul(G.gen, e)
     ctx.bases_free(h)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_scalar_mul_matches_oracle(ctx, group):
+    """hk_scalar_mul_* = the reference's `scalar_pairing` (pairing_ops.rs:32-39): out[i] = s_i * P_i, normalised.
+    Zero / one / r - 1 scalars, the point at infinity, canonical and Montgomery scalars."""
+    cv = ctx.curve
+    G = groups(cv.name)[group - 1]
+    rng = random.Random(60 + group)
+    enc, dec = ((codec.g1_affine_to_limbs, codec.g1_affine_from_limbs) if group == 1 else
+                (codec.g2_affine_to_limbs, codec.g2_affine_from_limbs))
+    pts = [G.mul(G.gen, rng.randrange(1, cv.r)) for _ in range(9)] + [None, G.gen]
+    sc = [0, 1, 2, cv.r - 1, 1 << 254 if cv.r > (1 << 254) else 1 << 253, 0xffffffff] + \
+         [rng.randrange(cv.r) for _ in range(3)] + [rng.randrange(cv.r), cv.r - 2]
+    limbs, inf = enc(pts, cv)
+    exp = [None if p is None else G.mul(p, s) for p, s in zip(pts, sc)]
+    out, oinf = ctx.scalar_mul(group, limbs, codec.ints_to_limbs(sc, 4), inf=inf)
+    assert dec(out, cv, oinf) == exp
+    out, oinf = ctx.scalar_mul(group, limbs, codec.to_mont(sc, cv.r, 4), inf=inf, repr_=B.SCALAR_MONT)
+    assert dec(out, cv, oinf) == exp
+    # twist-power pattern of the aggregator: P_i * r^i (aggregation.rs:225-242)
+    tw = rng.randrange(cv.r)
+    pw = [pow(tw, i, cv.r) for i in range(len(pts))]
+    out, oinf = ctx.scalar_mul(group, limbs, codec.ints_to_limbs(pw, 4), inf=inf)
+    assert dec(out, cv, oinf) == [None if p is None else G.mul(p, s) for p, s in zip(pts, pw)]
