@@ -323,7 +323,9 @@ def main():
         hz = hz.reshape(len(its), -1, 4)
         dz = torch.from_numpy(hz.view(np.int64)).to(dev)
         drsk = torch.from_numpy(np.concatenate([hr.ravel(), hs.ravel(), hk_.ravel()]).view(np.int64)).to(dev)
-        outs = [torch.zeros((per * (OUTB + COMB) + 63) // 8 + 4, dtype=torch.int64, device=dev) for _ in range(inflight)]
+        # one output record block per step of a run: the proofs of the whole job are gathered ONCE at its end
+        nout = max(args.steps, args.warmup, inflight, 4)
+        outs = [torch.zeros((per * (OUTB + COMB) + 63) // 8 + 4, dtype=torch.int64, device=dev) for _ in range(nout)]
         chunks.append(dict(hz=hz, hr=hr, hs=hs, hk=hk_, dz=dz, drsk=drsk, outs=outs, pins=pins))
     my_subcircuits = shard_range(args.batch * world, world, rank)      # contiguous chunk per rank (node.rs:471-493)
     assert len(my_subcircuits) == args.batch
@@ -333,20 +335,12 @@ def main():
         pp = pipes[i % inflight]
         for t, ch in enumerate(chunks):
             q = ch["drsk"].data_ptr()
-            p = ch["outs"][i % inflight].data_ptr()
+            p = ch["outs"][i % len(ch["outs"])].data_ptr()
             pc = p + ((per * OUTB + 15) // 16) * 16
             # stage 0: commitments (committer.rs:55-98); stage 1: proofs (committer.rs:100-122)
             pp["cctxs"][t].commit_batch_device(pk.handle, 0, per, ch["dz"].data_ptr(), wl.m, q + 64 * per, pc, pc + per * P1)
             pp["ctxs"][t].prove_batch_device(pk.handle, per, ch["dz"].data_ptr(), q, q + 32 * per, q + 64 * per,
                                              p, p + per * P1, p + per * (P1 + P2), p + per * (2 * P1 + P2))
-        if world > 1:
-            # the path's one exchange step: proof records to every rank (aggregation input), on the
-            # pipeline's first stream once its other streams are done
-            s0 = pp["pstreams"][0]
-            for s_ in pp["pstreams"][1:] + pp["cstreams"]:
-                s0.wait_stream(s_)
-            with torch.cuda.stream(s0):
-                gather_records(torch.cat([ch["outs"][i % inflight] for ch in chunks]).view(1, -1), world)
 
     import threading
 
@@ -357,6 +351,12 @@ def main():
             step_device(i)
         for s_ in all_streams:
             stream.wait_stream(s_)
+        if world > 1:
+            # the path's one exchange step (node.rs:687-715 gather_responses: once per stage, after every worker
+            # has finished its chunk): the proof records of the whole run go to every rank
+            with torch.cuda.stream(stream):
+                recs = [ch["outs"][i % len(ch["outs"])] for i in range(min(steps, len(chunks[0]["outs"]))) for ch in chunks]
+                gather_records(torch.cat(recs).view(1, -1), world)
 
     def run_host(steps):
         # host threads like the reference's per-proof OS threads (node.rs:745-795): per pipeline and
