@@ -14,6 +14,7 @@ from .curves import get_curve
 HK_HOST, HK_DEVICE, HK_HOST_PINNED = 0, 1, 2
 SCALAR_BIGINT, SCALAR_MONT = 0, 1
 NTT_FORWARD, NTT_INVERSE = 0, 1
+OPT_BA_ROUNDS, OPT_BA_MIN_ITEMS = 1, 2
 DOMAIN_PLAIN, DOMAIN_COSET = 0, 1
 FIELD_FR, FIELD_FQ, FIELD_FQ2 = 0, 1, 2
 FOP_MUL, FOP_ADD, FOP_SUB, FOP_INV, FOP_TO_MONT, FOP_FROM_MONT, FOP_INV_GCD, FOP_SQR = range(8)
@@ -61,6 +62,7 @@ def load_library(path=None):
         "hk_ctx_fork": [vp, vp, C.POINTER(vp)],
         "hk_bases_precompute": [vp, u64, u32],
         "hk_ctx_sync": [vp],
+        "hk_ctx_set_option": [vp, u32, u64],
         "hk_curve_info": [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)],
         "hk_bases_upload_g1": [vp, vp, u8p, sz, u32, C.POINTER(u64)],
         "hk_bases_upload_g2": [vp, vp, u8p, sz, u32, C.POINTER(u64)],
@@ -172,6 +174,10 @@ class Context:
     def _ck(self, rc):
         if rc != 0:
             raise HkError(rc, self.lib.hk_last_error_string(self.h).decode())
+
+    def set_option(self, option, value):
+        """hk_ctx_set_option: OPT_BA_ROUNDS (1), OPT_BA_MIN_ITEMS (2)."""
+        self._ck(self.lib.hk_ctx_set_option(self.h, option, value))
 
     def sync(self):
         self._ck(self.lib.hk_ctx_sync(self.h))

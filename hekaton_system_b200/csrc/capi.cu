@@ -329,6 +329,8 @@ HK_EXPORT int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx
     ctx->curve = curve;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->sh = std::make_shared<SharedState>();
+    if (const char* e = getenv("HK_BA_ROUNDS")) ctx->ba_rounds = atoi(e) < 0 ? 0 : (atoi(e) > 5 ? 5 : atoi(e));
+    if (const char* e = getenv("HK_BA_MIN")) ctx->ba_min_items = (size_t)atoll(e);
     if (cudaSetDevice(device) != cudaSuccess) {
         delete ctx;
         return HK_ERR_CUDA;
@@ -374,6 +376,8 @@ HK_EXPORT int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out) {
     ctx->curve = parent->curve;
     ctx->sm_count = parent->sm_count;
     ctx->sh = parent->sh;
+    ctx->ba_rounds = parent->ba_rounds;
+    ctx->ba_min_items = parent->ba_min_items;
     if (cudaSetDevice(ctx->device) != cudaSuccess) {
         delete ctx;
         return HK_ERR_CUDA;
@@ -394,6 +398,19 @@ HK_EXPORT int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out) {
     }
     *out = ctx;
     return HK_OK;
+}
+
+HK_EXPORT int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value) {
+    return guarded(ctx, [&] {
+        switch (option) {
+            case HK_OPT_BA_ROUNDS:
+                HK_REQUIRE(value <= 5, HK_ERR_INVALID, "HK_OPT_BA_ROUNDS must be 0..5");
+                ctx->ba_rounds = (int)value;
+                break;
+            case HK_OPT_BA_MIN_ITEMS: ctx->ba_min_items = (size_t)value; break;
+            default: throw HkError{HK_ERR_INVALID, "unknown option"};
+        }
+    });
 }
 
 HK_EXPORT int32_t hk_ctx_sync(hk_ctx* ctx) {

@@ -153,6 +153,9 @@ struct ProfRec {
 // of the same proof batch can run concurrently.
 struct MsmWs {
     DevBuf scalars, hist, items, buckets, chunks, wsum, scan, misc;
+    // batch-affine pre-reduction rounds (msm_impl.cuh): ping-pong point / pair lists,
+    // per-thread denominator products and the scratch of their batched inversion
+    DevBuf ba_pts[2], ba_pairs[2], ba_tot, ba_head, ba_pre, ba_lvl;
 };
 
 struct NttDomain;   // ntt.cu
@@ -198,6 +201,10 @@ struct hk_ctx {
     // serial_lanes (hk_profile_enable(ctx, 2)): every lane maps to the caller's stream, so kernels run one
     // at a time and the profiling events bracket each kernel alone (roofline measurements)
     bool serial_lanes = false;
+    // batch-affine pre-reduction rounds of the MSM (0 = off) and the list length from which they apply
+    // (0 = always); hk_ctx_set_option
+    int ba_rounds = 0;
+    size_t ba_min_items = size_t(1) << 20;
     cudaStream_t lane_stream(int lane) const { return !serial_lanes && lane > 0 && lane < LANES ? lane_ctl[lane] : stream; }
     cudaStream_t bulk_stream(int lane) const { return !serial_lanes && lane > 0 && lane < LANES ? lane_bulk[lane] : stream; }
     // stream used by the NTT / QAP kernels (normally the main stream; prove_run points it at the H lane)

@@ -258,45 +258,86 @@ inline void exclusive_scan_u32(hk_ctx* ctx, MsmWs& ws, cudaStream_t st, uint32_t
 // (key = 0xffffffff marks an empty slot).
 static constexpr uint32_t KEY_NONE = 0xffffffffu;
 
-template <class F, int S, int MINB>
+// SENT: the list comes from the batch-affine rounds (padding slots hold KEY_NONE, length = *d_count >> shift).
+template <class F, int S, int MINB, bool SENT>
 __global__ void __launch_bounds__(128, MINB)
 k_msm_accum(const Affine<F>* __restrict__ bases, const uint64_t* __restrict__ pairs,
-            const uint32_t* __restrict__ d_count, XYZZ<F>* buckets, XYZZ<F>* partial, uint32_t* partial_keys,
-            uint32_t nthreads) {
+            const uint32_t* __restrict__ d_count, uint32_t count_shift, XYZZ<F>* buckets, XYZZ<F>* partial,
+            uint32_t* partial_keys, uint32_t nthreads) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
-    uint32_t count = *d_count;
     size_t lo = (size_t)t * S;
     uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
-    if (lo < count) {
-        size_t hi = lo + S < count ? lo + S : count;
-        uint32_t cur = (uint32_t)(pairs[lo] >> 32);
-        uint32_t first_key = cur;
-        XYZZ<F> acc = XYZZ<F>::inf();
-        bool first_done = false;
-        for (size_t i = lo; i < hi; i++) {
-            const uint64_t pr = pairs[i];
-            uint32_t k = (uint32_t)(pr >> 32);
-            if (k != cur) {
+    if constexpr (!SENT) {
+        uint32_t count = *d_count;
+        if (lo < count) {
+            size_t hi = lo + S < count ? lo + S : count;
+            uint32_t cur = (uint32_t)(pairs[lo] >> 32);
+            uint32_t first_key = cur;
+            XYZZ<F> acc = XYZZ<F>::inf();
+            bool first_done = false;
+            for (size_t i = lo; i < hi; i++) {
+                const uint64_t pr = pairs[i];
+                uint32_t k = (uint32_t)(pr >> 32);
+                if (k != cur) {
+                    if (!first_done) {
+                        partial[2 * (size_t)t] = acc;
+                        first_done = true;
+                    } else {
+                        buckets[cur] = acc;
+                    }
+                    acc = XYZZ<F>::inf();
+                    cur = k;
+                }
+                uint32_t it = (uint32_t)pr;
+                Affine<F> p = bases[it >> 1];
+                acc.madd(p, it & 1);
+            }
+            k0 = first_key;
+            if (!first_done) {
+                partial[2 * (size_t)t] = acc;     // whole segment is one run
+            } else {
+                partial[2 * (size_t)t + 1] = acc;
+                k1 = cur;
+            }
+        }
+    } else {
+        const uint32_t count = *d_count >> count_shift;
+        if (lo < count) {
+            size_t hi = lo + S < count ? lo + S : count;
+            uint32_t cur = KEY_NONE, first_key = KEY_NONE;
+            XYZZ<F> acc = XYZZ<F>::inf();
+            bool first_done = false;
+            for (size_t i = lo; i < hi; i++) {
+                const uint64_t pr = pairs[i];
+                uint32_t k = (uint32_t)(pr >> 32);
+                if (k == KEY_NONE) continue;                  // padding slot
+                if (cur == KEY_NONE) {
+                    cur = k;
+                    first_key = k;
+                } else if (k != cur) {
+                    if (!first_done) {
+                        partial[2 * (size_t)t] = acc;
+                        first_done = true;
+                    } else {
+                        buckets[cur] = acc;
+                    }
+                    acc = XYZZ<F>::inf();
+                    cur = k;
+                }
+                uint32_t it = (uint32_t)pr;
+                Affine<F> p = bases[it >> 1];
+                acc.madd(p, it & 1);
+            }
+            if (cur != KEY_NONE) {
+                k0 = first_key;
                 if (!first_done) {
                     partial[2 * (size_t)t] = acc;
-                    first_done = true;
                 } else {
-                    buckets[cur] = acc;
+                    partial[2 * (size_t)t + 1] = acc;
+                    k1 = cur;
                 }
-                acc = XYZZ<F>::inf();
-                cur = k;
             }
-            uint32_t it = (uint32_t)pr;
-            Affine<F> p = bases[it >> 1];
-            acc.madd(p, it & 1);
-        }
-        k0 = first_key;
-        if (!first_done) {
-            partial[2 * (size_t)t] = acc;     // whole segment is one run
-        } else {
-            partial[2 * (size_t)t + 1] = acc;
-            k1 = cur;
         }
     }
     partial_keys[2 * (size_t)t] = k0;
@@ -351,6 +392,230 @@ k_msm_fold(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys,
     if (!final_level) {
         out_keys[2 * (size_t)t] = k0;
         out_keys[2 * (size_t)t + 1] = k1;
+    }
+}
+
+// ---- batch-affine pre-reduction ---------------------------------------------------------------
+// Before the XYZZ accumulation the key-sorted list is halved R times: in every round adjacent entries of the
+// same bucket are added pairwise IN AFFINE coordinates (lambda = (y2 - y1) / (x2 - x1), 2M + 1S) with ONE
+// shared inversion per round for the whole launch (Montgomery's trick: 3 more multiplications per addition),
+// i.e. 5M + 1S (+1M to recompute the prefix) instead of the 8M + 2S of a mixed XYZZ addition.  An inversion
+// costs 500+ multiplications, so it only pays when shared grid-wide:
+//   k_ba_prefix   every thread owns S consecutive slots, multiplies the denominators of its pairs -> tot[t]
+//   ba_invert     tot[] -> 1 / tot[] by a 64-ary product tree (forward), one GCD inversion per top-level
+//                 entry (a warp each, lane 0), and the tree backwards
+//   k_ba_apply    every thread recomputes its prefix products, walks its pairs backwards peeling off the
+//                 individual inverses, adds, and writes the round's output (odd leftovers pass through)
+// Layout: with the rounds enabled every bucket's run of the sorted list is padded to a multiple of 2^R slots
+// (the histogram counts are rounded up before the scan; unused slots hold the KEY_NONE sentinel).  Every run
+// then starts at a multiple of 2^R, so in EVERY round slot 2j pairs with slot 2j+1 and their sum lands in slot
+// j of the next list: no per-round offsets, no lookups, and all lanes of a warp take the same branch.
+// After R rounds (7/8 of the additions of long runs) the remaining list goes through k_msm_accum unchanged,
+// with the last round's points as its bases.
+enum : int { BA_ADD = 0, BA_DBL = 1, BA_INF = 2, BA_TAKE1 = 3, BA_TAKE2 = 4 };
+static constexpr uint64_t BA_EMPTY = ~0ull;      // pairs[] sentinel: key = KEY_NONE
+
+// classify p1 + p2 and return the denominator that the shared inversion has to cover (1 when none is needed)
+template <class F>
+__device__ __forceinline__ int ba_classify(const Affine<F>& p1, const Affine<F>& p2, F& d) {
+    d = F::one();
+    if (p1.is_inf()) return BA_TAKE2;
+    if (p2.is_inf()) return BA_TAKE1;
+    F dx = p2.x - p1.x;
+    if (!dx.is_zero()) {
+        d = dx;
+        return BA_ADD;
+    }
+    if (p1.y == p2.y) {          // same point: tangent, denominator 2y (y != 0: no 2-torsion in these groups)
+        d = p1.y.dbl();
+        return BA_DBL;
+    }
+    return BA_INF;               // p2 = -p1
+}
+
+template <class F>
+__device__ __forceinline__ Affine<F> ba_add(const Affine<F>& p1, const Affine<F>& p2, const F& inv_d, int kind) {
+    if (kind == BA_TAKE1) return p1;
+    if (kind == BA_TAKE2) return p2;
+    if (kind == BA_INF) return Affine<F>::inf();
+    F lam;
+    if (kind == BA_DBL) {
+        F x2 = p1.x.sqr();
+        lam = (x2.dbl() + x2) * inv_d;
+    } else {
+        lam = (p2.y - p1.y) * inv_d;
+    }
+    F x3 = lam.sqr() - p1.x - p2.x;
+    F y3 = lam * (p1.x - x3) - p1.y;
+    return {x3, y3};
+}
+
+template <class F>
+__device__ __forceinline__ Affine<F> ba_load(const Affine<F>* __restrict__ pts, uint32_t item) {
+    Affine<F> p = pts[item >> 1];
+    if ((item & 1u) && !p.is_inf()) p.y = p.y.neg();
+    return p;
+}
+
+// hist[k] = cnt rounded up to a multiple of 2^R (before the scan)
+static __global__ void k_ba_pad_counts(uint32_t* hist, size_t nkeys, uint32_t mask) {
+    size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k < nkeys) hist[k] = (hist[k] + mask) & ~mask;
+}
+static __global__ void k_ba_fill_empty(uint64_t* pairs, const uint32_t* __restrict__ d_n) {
+    const size_t n = *d_n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        pairs[i] = BA_EMPTY;
+}
+
+// Denominator of pair (p1, p2) from as little data as possible: the x coordinates decide almost always.
+template <class F>
+__device__ __forceinline__ F ba_denominator(const Affine<F>* __restrict__ pts, uint32_t it1, uint32_t it2) {
+    const Affine<F>* a = pts + (it1 >> 1);
+    const Affine<F>* b = pts + (it2 >> 1);
+    F x1 = a->x, x2 = b->x;
+    F dx = x2 - x1;
+    if (!dx.is_zero() && !x1.is_zero() && !x2.is_zero()) return dx;      // generic addition
+    // rare: equal x (doubling or P - P) or a possible point at infinity (x = 0): decide on the full points
+    Affine<F> p1 = ba_load(pts, it1), p2 = ba_load(pts, it2);
+    F d;
+    ba_classify(p1, p2, d);
+    return d;
+}
+
+// n slots this round = *d_n >> shift (the padded total of the sort, halved once per earlier round).
+// Thread t owns slots [t S, (t+1) S) = S/2 pair positions; pre[j * nthreads + t] = product of the denominators
+// of its pair positions before j (1 for positions that hold no addition), tot[t] = the product of all of them.
+template <class F, int S>
+__global__ void __launch_bounds__(128)
+k_ba_prefix(const Affine<F>* __restrict__ pts, const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ d_n,
+            uint32_t shift, F* pre, F* tot, uint32_t nthreads) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    const size_t n = *d_n >> shift;
+    F acc = F::one();
+    size_t lo = (size_t)t * S;
+    if (lo < n) {
+        const uint64_t* pp = pairs + lo;
+#pragma unroll 2
+        for (int j = 0; j < S / 2; j++) {
+            if (lo + 2 * j >= n) break;
+            const uint64_t pa = pp[2 * j], pb = pp[2 * j + 1];
+            pre[(size_t)j * nthreads + t] = acc;
+            if (pb == BA_EMPTY) continue;                 // empty pair or odd leftover (pa valid, pb empty)
+            acc = acc * ba_denominator(pts, (uint32_t)pa, (uint32_t)pb);
+        }
+    }
+    tot[t] = acc;
+}
+
+template <class F, int S>
+__global__ void __launch_bounds__(128)
+k_ba_apply(const Affine<F>* __restrict__ pts, const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ d_n,
+           uint32_t shift, const F* __restrict__ pre, const F* __restrict__ inv_tot, Affine<F>* out_pts,
+           uint64_t* out_pairs, uint32_t nthreads) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    const size_t n = *d_n >> shift;
+    size_t lo = (size_t)t * S;
+    if (lo >= n) return;
+    const uint64_t* pp = pairs + lo;
+    F inv = inv_tot[t];          // 1 / (product of all denominators of this thread)
+#pragma unroll 2
+    for (int j = S / 2 - 1; j >= 0; j--) {
+        if (lo + 2 * j >= n) continue;
+        const uint64_t pa = pp[2 * j], pb = pp[2 * j + 1];
+        const size_t slot = (lo >> 1) + j;
+        if (pb == BA_EMPTY) {                             // nothing to add: empty pair, or an odd leftover passes through
+            if (pa == BA_EMPTY) {
+                out_pairs[slot] = BA_EMPTY;
+            } else {
+                out_pts[slot] = ba_load(pts, (uint32_t)pa);
+                out_pairs[slot] = (pa & 0xffffffff00000000ull) | ((uint64_t)slot << 1);
+            }
+            continue;
+        }
+        Affine<F> p1 = ba_load(pts, (uint32_t)pa);
+        Affine<F> p2 = ba_load(pts, (uint32_t)pb);
+        F d;
+        const int kind = ba_classify(p1, p2, d);
+        F inv_d = inv * pre[(size_t)j * nthreads + t];
+        inv = inv * d;
+        out_pts[slot] = ba_add(p1, p2, inv_d, kind);
+        out_pairs[slot] = (pa & 0xffffffff00000000ull) | ((uint64_t)slot << 1);
+    }
+}
+
+// forward level of the product tree: groups of 64 consecutive values; pre[i] = product of the group's
+// values before i (exclusive), group_tot[g] = product of the whole group
+template <class F>
+__global__ void __launch_bounds__(128)
+k_ba_tree_fwd(const F* __restrict__ vals, size_t n, F* pre, F* group_tot) {
+    size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t lo = g * 64;
+    if (lo >= n) return;
+    size_t hi = lo + 64 < n ? lo + 64 : n;
+    F acc = F::one();
+    for (size_t i = lo; i < hi; i++) {
+        pre[i] = acc;
+        acc = acc * vals[i];
+    }
+    group_tot[g] = acc;
+}
+// backward level: group_inv[g] = 1 / (product of the group) -> vals[i] = 1 / vals[i]
+template <class F>
+__global__ void __launch_bounds__(128)
+k_ba_tree_bwd(F* vals, size_t n, const F* __restrict__ pre, const F* __restrict__ group_inv) {
+    size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t lo = g * 64;
+    if (lo >= n) return;
+    size_t hi = lo + 64 < n ? lo + 64 : n;
+    F inv = group_inv[g];
+    for (size_t i = hi; i-- > lo;) {
+        F v = vals[i];
+        vals[i] = inv * pre[i];
+        inv = inv * v;
+    }
+}
+// top of the tree: one warp per value (lane 0 works: the GCD inversion's branches must not serialise)
+template <class F>
+__global__ void __launch_bounds__(128)
+k_ba_invert_top(F* vals, size_t n) {
+    size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g & 31) return;
+    size_t i = g >> 5;
+    if (i < n) vals[i] = vals[i].inverse_fast();
+}
+
+// vals[0..n) -> their inverses, in place (no value may be zero)
+template <class F>
+void ba_invert(hk_ctx* ctx, MsmWs& ws, cudaStream_t st, F* vals, size_t n) {
+    std::vector<size_t> sizes{n};
+    while (sizes.back() > 1024) sizes.push_back((sizes.back() + 63) / 64);
+    size_t pre_total = 0, lvl_total = 0;
+    for (size_t l = 0; l + 1 < sizes.size(); l++) pre_total += sizes[l], lvl_total += sizes[l + 1];
+    F* pre = ws.ba_pre.as<F>(pre_total + 1);
+    F* lvl = ws.ba_lvl.as<F>(lvl_total + 1);
+    std::vector<F*> v{vals}, p;
+    {
+        F* pp = pre;
+        F* ll = lvl;
+        for (size_t l = 0; l + 1 < sizes.size(); l++) {
+            p.push_back(pp);
+            pp += sizes[l];
+            v.push_back(ll);
+            ll += sizes[l + 1];
+        }
+    }
+    for (size_t l = 0; l + 1 < sizes.size(); l++) {
+        k_ba_tree_fwd<F><<<ceil_div(sizes[l + 1], 128), 128, 0, st>>>(v[l], sizes[l], p[l], v[l + 1]);
+        HK_LAUNCH_CHECK(ctx);
+    }
+    k_ba_invert_top<F><<<ceil_div(sizes.back() * 32, 128), 128, 0, st>>>(v.back(), sizes.back());
+    HK_LAUNCH_CHECK(ctx);
+    for (size_t l = sizes.size() - 1; l-- > 0;) {
+        k_ba_tree_bwd<F><<<ceil_div(sizes[l + 1], 128), 128, 0, st>>>(v[l], sizes[l], p[l], v[l + 1]);
+        HK_LAUNCH_CHECK(ctx);
     }
 }
 
@@ -501,9 +766,8 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     // level-0 segment length / occupancy variant (HK_ACCUM_S in {32,64,128}, HK_ACCUM_MINB in {2,3,4}, default 4:
     // with the call-based multiply 4 CTAs/SM at 128 registers beat 2 at 206 -- profiles/r01c;
     // G2 always uses MINB = 1)
-    static const int env_s = getenv("HK_ACCUM_S") ? atoi(getenv("HK_ACCUM_S")) : 32;
     static const int env_minb = getenv("HK_ACCUM_MINB") ? atoi(getenv("HK_ACCUM_MINB")) : 4;
-    const int S0 = (env_s == 64 || env_s == 128) ? env_s : 32;
+    constexpr int S0 = 32;   // level-0 segment length (64 / 128 measured slower: profiles/r01c)
     constexpr int S1 = 16;   // fold segment length
 
     const Scalar256* d_sc = d_scalars_in;
@@ -522,11 +786,26 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
         d_sc = conv;
         sc_stride = n;
     }
+    // batch-affine pre-reduction: OFF by default (hk_ctx_set_option HK_OPT_BA_ROUNDS / HK_OPT_BA_MIN_ITEMS, or the
+    // HK_BA_ROUNDS / HK_BA_MIN environment defaults).  Measured on B200 (profiles/r01e_batch_affine.md): a round costs
+    // 2.58 ms per 8.4 M additions against 2.92 ms for the XYZZ kernel (+13 %), but adds ~0.65 ms of inversion-tree
+    // latency per round and leaves a short, latency-bound list to the accumulation -- a wash in the proof
+    // pipeline (275 vs 274 proofs/s) and a loss for a standalone MSM (9.1 vs 8.0 ms at 2^20).
+    constexpr int BA_S = 32;           // slots per thread in the batch-affine kernels
+    const int env_ba_rounds = ctx->ba_rounds;
+    const bool ba_on = env_ba_rounds > 0 &&
+                       (ctx->ba_min_items == 0 || (max_items >= ctx->ba_min_items && max_items / nkeys >= 8));
+    const int ba_rounds = ba_on ? (env_ba_rounds < 1 ? 1 : (env_ba_rounds > 5 ? 5 : env_ba_rounds)) : 0;
+    // with the rounds on, every bucket's run is padded to a multiple of 2^R slots
+    const uint32_t ba_mask = (1u << ba_rounds) - 1u;
+    const size_t list_ub = ba_rounds ? ((max_items + (size_t)ba_mask * nkeys + ba_mask) & ~(size_t)ba_mask) : max_items;
+    HK_REQUIRE(list_ub < (size_t(1) << 32), HK_ERR_UNSUPPORTED, "msm: padded item list must be < 2^32");
+    const size_t acc_ub = list_ub >> ba_rounds;      // upper bound of the list length the accumulation kernel sees
     uint32_t* hist = ws.hist.as<uint32_t>(nkeys + 4);
     uint32_t* d_count = hist + nkeys;     // total item count lives right after the histogram
-    uint64_t* pairs = ws.items.as<uint64_t>(max_items);
+    uint64_t* pairs = ws.items.as<uint64_t>(list_ub + 2);
     XYZZ<F>* buckets = ws.buckets.as<XYZZ<F>>(nkeys);
-    const uint32_t nthr0 = ceil_div(max_items, S0);
+    const uint32_t nthr0 = ceil_div(acc_ub, S0);
     std::vector<uint32_t> lvl_in;      // entries consumed at fold level l
     {
         uint32_t cur = 2 * nthr0;
@@ -557,7 +836,15 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     const uint8_t* skip = bv.skip ? bv.skip + offset : nullptr;
     k_msm_hist<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window, skip, hist);
     HK_LAUNCH_CHECK(ctx);
+    if (ba_rounds) {
+        k_ba_pad_counts<<<ceil_div(nkeys, 256), 256, 0, st>>>(hist, nkeys, ba_mask);
+        HK_LAUNCH_CHECK(ctx);
+    }
     exclusive_scan_u32(ctx, ws, st, hist, nkeys, d_count);
+    if (ba_rounds) {
+        k_ba_fill_empty<<<ctx->sm_count * 8, 256, 0, st>>>(pairs, d_count);
+        HK_LAUNCH_CHECK(ctx);
+    }
     k_msm_scatter<<<ceil_div(n * K, 256), 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, Wred, per_window,
                                                         item_stride, skip, hist, pairs);
     HK_LAUNCH_CHECK(ctx);
@@ -565,17 +852,43 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
         HK_CUDA(cudaEventRecord(ctx->ev_sorted[lane], st));
         HK_CUDA(cudaStreamWaitEvent(sb, ctx->ev_sorted[lane], 0));
     }
+    const Affine<F>* acc_bases = d_bases;
+    const uint64_t* acc_pairs = pairs;
+    for (int r = 0; r < ba_rounds; r++) {
+        const size_t n_ub = list_ub >> r;
+        const uint32_t nthr = ceil_div(n_ub, BA_S);
+        F* tot = ws.ba_tot.as<F>(nthr);
+        F* pre = ws.ba_head.as<F>((size_t)nthr * (BA_S / 2));
+        Affine<F>* out_pts = ws.ba_pts[r & 1].as<Affine<F>>((n_ub >> 1) + 1);
+        uint64_t* out_pairs = ws.ba_pairs[r & 1].as<uint64_t>((n_ub >> 1) + 2);
+        int pb = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_BA_G1 : HK_PROF_MSM_BA_G2, sb);
+        k_ba_prefix<F, BA_S><<<ceil_div(nthr, 128), 128, 0, sb>>>(acc_bases, acc_pairs, d_count, (uint32_t)r, pre, tot, nthr);
+        HK_LAUNCH_CHECK(ctx);
+        ba_invert<F>(ctx, ws, sb, tot, nthr);
+        k_ba_apply<F, BA_S><<<ceil_div(nthr, 128), 128, 0, sb>>>(acc_bases, acc_pairs, d_count, (uint32_t)r, pre, tot, out_pts,
+                                                                out_pairs, nthr);
+        HK_LAUNCH_CHECK(ctx);
+        prof_end(ctx, pb, 0, d_count, sb);
+        acc_bases = out_pts;
+        acc_pairs = out_pairs;
+    }
     int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2, sb);
     {
         const dim3 grid(ceil_div(nthr0, 128));
-#define HK_ACC(SS, MB) k_msm_accum<F, SS, MB><<<grid, 128, 0, sb>>>(d_bases, pairs, d_count, buckets, partial, partial_keys, nthr0)
+#define HK_ACC(SS, MB)                                                                                               \
+    do {                                                                                                            \
+        if (ba_rounds)                                                                                              \
+            k_msm_accum<F, SS, MB, true><<<grid, 128, 0, sb>>>(acc_bases, acc_pairs, d_count, (uint32_t)ba_rounds, buckets, \
+                                                               partial, partial_keys, nthr0);                       \
+        else                                                                                                        \
+            k_msm_accum<F, SS, MB, false><<<grid, 128, 0, sb>>>(acc_bases, acc_pairs, d_count, 0u, buckets, partial, \
+                                                                partial_keys, nthr0);                               \
+    } while (0)
         if constexpr (GROUP == 2) {
-            if (S0 == 32) HK_ACC(32, 1); else if (S0 == 64) HK_ACC(64, 1); else HK_ACC(128, 1);
+            HK_ACC(32, 1);
         } else {
             const int mb = env_minb;
-            if (S0 == 32) { if (mb == 3) HK_ACC(32, 3); else if (mb == 4) HK_ACC(32, 4); else HK_ACC(32, 2); }
-            else if (S0 == 64) { if (mb == 3) HK_ACC(64, 3); else if (mb == 4) HK_ACC(64, 4); else HK_ACC(64, 2); }
-            else { if (mb == 3) HK_ACC(128, 3); else if (mb == 4) HK_ACC(128, 4); else HK_ACC(128, 2); }
+            if (mb == 3) HK_ACC(32, 3); else if (mb == 2) HK_ACC(32, 2); else HK_ACC(32, 4);
         }
 #undef HK_ACC
     }

@@ -88,6 +88,12 @@ int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx** out);
  * Handle-table access is mutex-protected; each context is still single-threaded. */
 int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out);
 int32_t hk_ctx_destroy(hk_ctx* ctx);
+/* Tuning knobs of a context (forks inherit them at fork time).
+ *   HK_OPT_BA_ROUNDS     batch-affine pre-reduction rounds of the MSM bucket accumulation, 0..5 (default 0 = off;
+ *                        same results)
+ *   HK_OPT_BA_MIN_ITEMS  apply them only to MSMs whose digit list can reach this length (default 2^20; 0 = always) */
+enum { HK_OPT_BA_ROUNDS = 1, HK_OPT_BA_MIN_ITEMS = 2 };
+int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value);
 int32_t hk_ctx_sync(hk_ctx* ctx);
 const char* hk_last_error_string(hk_ctx* ctx);
 /* Limb counts for this context's curve (fq_limbs64 = 6 or 4; fr_limbs64 = 4). */
@@ -237,7 +243,9 @@ int32_t hk_bench_field_mul(hk_ctx* ctx, uint32_t field, uint32_t threads, uint32
  *         includes the time it shares the GPU with others);
  * on = 2: additionally serialise the lanes of hk_commit* / hk_prove* onto the context stream, so that every
  *         launch is timed alone (same kernels, same inputs; the batch itself runs slower). */
-enum { HK_PROF_MSM_ACCUM_G1 = 0, HK_PROF_MSM_ACCUM_G2 = 1, HK_PROF_NTT_PASS = 2, HK_PROF_COUNT = 3 };
+enum { HK_PROF_MSM_ACCUM_G1 = 0, HK_PROF_MSM_ACCUM_G2 = 1, HK_PROF_NTT_PASS = 2,
+       HK_PROF_MSM_BA_G1 = 3, HK_PROF_MSM_BA_G2 = 4 /* batch-affine round (prefix + inversion + apply); units = entries in */,
+       HK_PROF_COUNT = 5 };
 int32_t hk_profile_enable(hk_ctx* ctx, int32_t on);
 int32_t hk_profile_reset(hk_ctx* ctx);
 int32_t hk_profile_read(hk_ctx* ctx, uint32_t kernel_id, double* total_ms, uint64_t* launches, uint64_t* units);

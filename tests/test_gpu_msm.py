@@ -237,3 +237,50 @@ def test_scalar_mul_matches_oracle(ctx, group):
     pw = [pow(tw, i, cv.r) for i in range(len(pts))]
     out, oinf = ctx.scalar_mul(group, limbs, codec.ints_to_limbs(pw, 4), inf=inf)
     assert dec(out, cv, oinf) == [None if p is None else G.mul(p, s) for p, s in zip(pts, pw)]
+
+
+@pytest.mark.parametrize("rounds", [1, 3])
+def test_batch_affine_rounds_give_identical_results(ctx, rounds):
+    """HK_OPT_BA_ROUNDS (off by default): the batch-affine pre-reduction must not change any result.  Forced on
+    for every MSM of a forked context and run over the cases that stress it: runs of every length 0..40 in one
+    bucket (odd leftovers, padding), P + P, P - P, bases at infinity, uniform and witness-like scalars, G1 / G2,
+    table and plain mode, a batch."""
+    cv = ctx.curve
+    f = ctx.fork()
+    f.set_option(B.OPT_BA_ROUNDS, rounds)
+    f.set_option(B.OPT_BA_MIN_ITEMS, 0)
+    rng = random.Random(900 + rounds)
+    try:
+        for group in (1, 2):
+            G = groups(cv.name)[group - 1]
+            n = 700 if group == 1 else 200
+            pts = [G.mul(G.gen, rng.randrange(1, cv.r)) for _ in range(n // 4)]
+            pts = pts + pts[: n // 8] + [G.neg(p) for p in pts[: n // 8]] + [None] * 5      # duplicates, negations, infinity
+            while len(pts) < n:
+                pts.append(G.mul(G.gen, rng.randrange(1, cv.r)))
+            rng.shuffle(pts)
+            h = _upload(f, group, pts)
+            for table in (False, True):
+                if table:
+                    f.bases_precompute(h)
+                for kind in range(4):
+                    if kind == 0:
+                        sc = [rng.randrange(cv.r) for _ in range(n)]
+                    elif kind == 1:          # every scalar small: a few buckets with long runs of every length
+                        sc = [rng.randrange(0, 6) for _ in range(n)]
+                    elif kind == 2:          # one bucket only
+                        sc = [1] * n
+                    else:
+                        sc = [rng.randrange(2) if rng.random() < 0.9 else rng.randrange(cv.r) for _ in range(n)]
+                    assert _msm_affine(f, group, h, sc) == G.msm_naive(pts, sc), (group, table, kind)
+            # runs of length 0..40 of the same point in bucket 1: sum = L * P
+            for L_ in (0, 1, 2, 3, 7, 8, 9, 31, 32, 33, 40):
+                sc = [1] * L_ + [0] * (n - L_)
+                acc = None
+                for p_ in pts[:L_]:
+                    if p_ is not None:
+                        acc = G.add(acc, p_)
+                assert _msm_affine(f, group, h, sc) == acc, (group, L_)
+            f.bases_free(h)
+    finally:
+        f.close()
