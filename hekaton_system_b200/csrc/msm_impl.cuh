@@ -767,8 +767,17 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     // with the call-based multiply 4 CTAs/SM at 128 registers beat 2 at 206 -- profiles/r01c;
     // G2 always uses MINB = 1)
     static const int env_minb = getenv("HK_ACCUM_MINB") ? atoi(getenv("HK_ACCUM_MINB")) : 4;
-    constexpr int S0 = 32;   // level-0 segment length (64 / 128 measured slower: profiles/r01c)
-    constexpr int S1 = 16;   // fold segment length
+    // level-0 segment length: 32 (64 / 128 measured slower: profiles/r01c); a standalone MSM whose list cannot
+    // fill the GPU with 32-item segments (latency-bound 32-addition chains) uses 8
+    static const int env_s0 = getenv("HK_ACCUM_S") ? atoi(getenv("HK_ACCUM_S")) : 0;
+    const int S0 = env_s0 == 8 || env_s0 == 32 ? env_s0 : ((lane == 0 && n * K * (size_t)pl.W <= (size_t(1) << 21)) ? 8 : 32);
+    // fold segment length: short segments mean more levels (each halves the list) but a 4-addition serial chain
+    // per level instead of 16; measured per 2^20 G1 MSM 16 / 8 / 4 -> 7.83 / 7.66 / 7.64 ms, 2^16: 1.93 / 1.74 / 1.69,
+    // G2 2^18: 10.10 / 9.49 / 9.23 (HK_FOLD_S overrides)
+    // Inside a proof batch (lane != 0) the tails are hidden under other lanes' accumulations and the extra
+    // launches of short segments cost throughput (280 -> 264 proofs/s), so only standalone MSMs use 4.
+    static const int env_s1 = getenv("HK_FOLD_S") ? atoi(getenv("HK_FOLD_S")) : 0;
+    const int S1 = (env_s1 == 4 || env_s1 == 8 || env_s1 == 16 || env_s1 == 32) ? env_s1 : (lane == 0 ? 4 : 16);
 
     const Scalar256* d_sc = d_scalars_in;
     if (scalars_mont) {
@@ -821,7 +830,12 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
     XYZZ<F>* partial = ws.chunks.as<XYZZ<F>>(part_total);
     uint32_t* partial_keys = ws.misc.as<uint32_t>(part_total);
     // reduction geometry: short serial chunks, then a multi-block tree
-    uint32_t G = pl.B >= 32768 ? 8 : (pl.B >= 1024 ? 4 : (pl.B >= 64 ? 2 : 1));
+    static const int env_g = getenv("HK_REDUCE_G") ? atoi(getenv("HK_REDUCE_G")) : 0;
+    // standalone (lane 0): short chunks shorten the serial tail (8 / 4 / 2 / 1 at B = 32768 -> 7.97 / 7.88 / 7.86 / 7.95 ms
+    // per 2^20 MSM); inside a proof batch the 4x larger grids of a latency-bound kernel take SM slots from the
+    // accumulations (283 -> 269 proofs/s), so the lanes keep long chunks
+    uint32_t G = lane == 0 ? (pl.B >= 64 ? 2 : 1) : (pl.B >= 32768 ? 8 : (pl.B >= 1024 ? 4 : (pl.B >= 64 ? 2 : 1)));
+    if (env_g > 0 && (uint32_t)env_g <= pl.B) G = (uint32_t)env_g;
     uint32_t T = pl.B / G;
     constexpr int TS_TPB = 64;
     static_assert(TS_TPB * sizeof(XYZZ<F>) <= 48 * 1024, "tree-sum tile must fit the default dynamic smem limit");
@@ -885,10 +899,11 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
                                                                 partial_keys, nthr0);                               \
     } while (0)
         if constexpr (GROUP == 2) {
-            HK_ACC(32, 1);
+            if (S0 == 8) HK_ACC(8, 1); else HK_ACC(32, 1);
         } else {
             const int mb = env_minb;
-            if (mb == 3) HK_ACC(32, 3); else if (mb == 2) HK_ACC(32, 2); else HK_ACC(32, 4);
+            if (S0 == 8) HK_ACC(8, 4);
+            else if (mb == 3) HK_ACC(32, 3); else if (mb == 2) HK_ACC(32, 2); else HK_ACC(32, 4);
         }
 #undef HK_ACC
     }
@@ -907,7 +922,10 @@ void msm_run(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, const Sca
         uint32_t* in_keys = partial_keys + off;
         XYZZ<F>* out = partial + off + n_in;
         uint32_t* out_keys = partial_keys + off + n_in;
-        k_msm_fold<F, S1><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
+        if (S1 == 8) k_msm_fold<F, 8><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
+        else if (S1 == 4) k_msm_fold<F, 4><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
+        else if (S1 == 32) k_msm_fold<F, 32><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
+        else k_msm_fold<F, 16><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
         HK_LAUNCH_CHECK(ctx);
         off += n_in;
     }
