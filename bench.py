@@ -11,8 +11,9 @@ n = 200 000 constraints, domain N = 2^18, BLS12-381), `--batch` subcircuits per 
 subcircuits are independent, so ranks shard them with no data-path collective and only gather
 the finished proofs (weak scaling).  One JSON line is printed by rank 0:
   value  proofs/s with every input already resident in HBM (hk_prove, HK_DEVICE)
-  e2e    proofs/s through the host-buffer C-ABI call (hk_prove, HK_HOST): H2D of the
-         assignment and D2H of the proof inside the timed region
+  e2e    proofs/s through the host-buffer C-ABI calls (hk_commit_batch / hk_prove_batch,
+         HK_HOST_PINNED_ASYNC): H2D of the assignments from pinned host memory and D2H of the commitments
+         and proofs inside the timed region
   roofline      dominant kernel (G1 bucket accumulation), integer-multiply bound
   roofline_ntt  NTT passes against measured HBM bandwidth (north_star's figure)
   cpu_baseline  the oracle's C restatement of the reference prover (arkworks-0.4 algorithms) on
@@ -53,6 +54,8 @@ def parse():
                     help="BASELINE config 2 instead of the proof bench: checked G1/G2 MSM + Fr NTT sweep 2^16..2^24 "
                          "(tools/sweep.py; one JSON line per point)")
     ap.add_argument("--sweep-args", default="", help="extra arguments for tools/sweep.py")
+    ap.add_argument("--timeline-host", action="store_true",
+                    help="with --timeline: profile the end-to-end (host-buffer) path instead of the device-resident one")
     ap.add_argument("--timeline", default=None,
                     help="diagnostic: write the kernel timeline (name, stream, start, duration) of ONE warm step to "
                          "this file (torch.profiler / CUPTI) and exit; prints no bench line")
@@ -359,22 +362,35 @@ def main():
                 recs = [ch["outs"][i % len(ch["outs"])] for i in range(min(steps, len(chunks[0]["outs"]))) for ch in chunks]
                 gather_records(torch.cat(recs).view(1, -1), world)
 
-    def run_host(steps):
-        # host threads like the reference's per-proof OS threads (node.rs:745-795): per pipeline and
-        # sub-batch one thread for the commitments and one for the proofs; every call copies its
-        # inputs H2D from pinned memory, computes, and copies the result back (blocking)
-        def work(j, t, kind):
-            pp, ch = pipes[j], chunks[t]
-            for _ in range(j, steps, inflight):
-                if kind == 0:
-                    pp["cctxs"][t].commit_batch(pk.handle, 0, ch["hz"], ch["hk"])
-                else:
-                    pp["ctxs"][t].prove_batch(pk.handle, ch["hz"], ch["hr"], ch["hs"], ch["hk"], pinned=True)
+    # pinned output blocks for the end-to-end path, one per step of a run
+    def pinned_u64(*shape):
+        return torch.zeros(shape, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
 
-        ths = [threading.Thread(target=work, args=(j, t, kind)) for j in range(inflight) for t in range(nstreams)
-               for kind in (0, 1)]
-        [t.start() for t in ths]
-        [t.join() for t in ths]
+    nhost = max(args.steps, 2 * inflight, 4)
+    for ch in chunks:
+        ch["hout"] = [dict(a=pinned_u64(per, 2 * L), b=pinned_u64(per, 4 * L), c=pinned_u64(per, 2 * L),
+                           inf=torch.zeros((per, 3), dtype=torch.uint8).pin_memory().numpy(),
+                           com=pinned_u64(per, 2 * L), cinf=torch.zeros(per, dtype=torch.uint8).pin_memory().numpy())
+                      for _ in range(nhost)]
+
+    def run_host(steps):
+        # End to end through the host-buffer C ABI (HK_HOST_PINNED_ASYNC): every step's assignments are DMA'd from
+        # pinned host memory and its commitments / proofs are DMA'd back into pinned host memory, all inside the timed
+        # region.  The calls only enqueue, so the upload of a batch overlaps the kernels of the previous one and
+        # `inflight` batches overlap like in the device-resident run; one sync per context at the end.
+        for s_ in all_streams:
+            s_.wait_stream(stream)
+        for i in range(steps):
+            pp = pipes[i % inflight]
+            for t, ch in enumerate(chunks):
+                o = ch["hout"][i % nhost]
+                pp["cctxs"][t].commit_batch_async(pk.handle, 0, ch["hz"], ch["hk"], o["com"], o["cinf"])
+                pp["ctxs"][t].prove_batch_async(pk.handle, ch["hz"], ch["hr"].reshape(per, 4), ch["hs"].reshape(per, 4),
+                                                ch["hk"].reshape(per, -1, 4), o["a"], o["b"], o["c"], o["inf"])
+        for c_ in all_ctxs:
+            c_.sync()
+        for s_ in all_streams:
+            stream.wait_stream(s_)
 
     def timed(fn, steps):
         if world > 1:
@@ -412,8 +428,13 @@ def main():
     torch.cuda.synchronize()
     if args.timeline:
         from torch.profiler import ProfilerActivity, profile
+        if args.timeline_host:
+            run_host(2 * inflight)
         with profile(activities=[ProfilerActivity.CUDA]) as tp:
-            run_device(inflight)
+            if args.timeline_host:
+                run_host(2 * inflight)
+            else:
+                run_device(inflight)
             torch.cuda.synchronize()
         tmp = args.timeline + ".chrome.json"
         tp.export_chrome_trace(tmp)

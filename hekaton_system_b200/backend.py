@@ -11,7 +11,7 @@ import numpy as np
 
 from .curves import get_curve
 
-HK_HOST, HK_DEVICE, HK_HOST_PINNED = 0, 1, 2
+HK_HOST, HK_DEVICE, HK_HOST_PINNED, HK_HOST_PINNED_ASYNC = 0, 1, 2, 3
 SCALAR_BIGINT, SCALAR_MONT = 0, 1
 NTT_FORWARD, NTT_INVERSE = 0, 1
 OPT_BA_ROUNDS, OPT_BA_MIN_ITEMS = 1, 2
@@ -397,6 +397,21 @@ class Context:
                                          HK_HOST_PINNED if pinned else HK_HOST, a.ctypes.data,
                                          b.ctypes.data, c.ctypes.data, inf.ctypes.data))
         return a, b, c, inf
+
+    def prove_batch_async(self, pk, z, r, s, kappas, a, b, c, inf):
+        """HK_HOST_PINNED_ASYNC: every argument is a numpy view of PAGE-LOCKED memory (inputs z (K, m, 4), r, s
+        (K, 4), kappas (K, ns-1, 4); outputs a (K, 2L), b (K, 4L), c (K, 2L), inf (K, 3) uint8).  Only enqueues;
+        the outputs are valid after `sync()`.  Several calls may be in flight."""
+        K = z.shape[0]
+        self._ck(self.lib.hk_prove_batch(self.h, pk, K, z.ctypes.data, r.ctypes.data, s.ctypes.data,
+                                         kappas.ctypes.data if kappas.size else None, HK_HOST_PINNED_ASYNC,
+                                         a.ctypes.data, b.ctypes.data, c.ctypes.data, inf.ctypes.data))
+
+    def commit_batch_async(self, pk, stage, z, kappa, out, inf):
+        """HK_HOST_PINNED_ASYNC commitments: page-locked z (K, m, 4), kappa (K, 4) in, out (K, 2L), inf (K,) out;
+        valid after `sync()`."""
+        self._ck(self.lib.hk_commit_batch(self.h, pk, stage, z.shape[0], z.ctypes.data, z.shape[1], kappa.ctypes.data,
+                                          HK_HOST_PINNED_ASYNC, out.ctypes.data, inf.ctypes.data))
 
     def prove_batch_device(self, pk, K, z, r, s, kappas, a, b, c, inf):
         """Device pointers (z K*m, r K, s K, kappas K*(ns-1); outputs K each); asynchronous."""

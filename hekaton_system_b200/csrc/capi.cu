@@ -362,6 +362,14 @@ HK_EXPORT int32_t hk_ctx_destroy(hk_ctx* ctx) {
     ctx->sh.reset();     // shared resources are freed with the last context that references them
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     ctx_free_side(ctx);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(ctx->ev_h2d[i]);
+            cudaEventDestroy(ctx->ev_in_free[i]);
+        }
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HK_OK;
@@ -691,6 +699,16 @@ HK_EXPORT int32_t hk_pk_free(hk_ctx* ctx, uint64_t pk_handle) {
     });
 }
 
+// copy stream + events of the asynchronous host-buffer path, created on first use
+static void async_streams(hk_ctx* ctx) {
+    if (ctx->copy_stream) return;
+    HK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        HK_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+        HK_CUDA(cudaEventCreateWithFlags(&ctx->ev_in_free[i], cudaEventDisableTiming));
+    }
+}
+
 HK_EXPORT int32_t hk_commit_batch(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, size_t K, const uint64_t* z,
                                   size_t z_stride, const uint64_t* kappa, uint32_t memspace, void* com_affine,
                                   uint8_t* com_inf) {
@@ -712,6 +730,10 @@ HK_EXPORT int32_t hk_commit_batch(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, si
                      [&] { commit_run<Bn254>(ctx, pk, stage, K, z, z_stride, kappa, com_affine, com_inf); });
             return;
         }
+        HK_REQUIRE(memspace == HK_HOST || memspace == HK_HOST_PINNED || memspace == HK_HOST_PINNED_ASYNC, HK_ERR_INVALID,
+                   "bad memspace");
+        const bool async = memspace == HK_HOST_PINNED_ASYNC;
+        HK_REQUIRE(!async || com_inf, HK_ERR_INVALID, "com_inf is NULL");
         // host: only the committed prefix of every assignment is copied (stride `need` on the device)
         char* dz = (char*)ctx->ws_z.ensure(K * need * 32 + K * 32 + 64);
         for (size_t k = 0; k < K; k++)
@@ -725,6 +747,10 @@ HK_EXPORT int32_t hk_commit_batch(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, si
                  [&] { commit_run<Bls12381>(ctx, pk, stage, K, (const uint64_t*)dz, need, (const uint64_t*)dk, d_out, d_inf); },
                  [&] { commit_run<Bn254>(ctx, pk, stage, K, (const uint64_t*)dz, need, (const uint64_t*)dk, d_out, d_inf); });
         HK_CUDA(cudaMemcpyAsync(com_affine, d_out, K * pb, cudaMemcpyDeviceToHost, ctx->stream));
+        if (async) {      // stream-ordered: the next call's uploads into ws_z queue behind these kernels
+            HK_CUDA(cudaMemcpyAsync(com_inf, d_inf, K, cudaMemcpyDeviceToHost, ctx->stream));
+            return;
+        }
         std::vector<uint8_t> tmp(K);
         HK_CUDA(cudaMemcpyAsync(tmp.data(), d_inf, K, cudaMemcpyDeviceToHost, ctx->stream));
         HK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -761,6 +787,39 @@ HK_EXPORT int32_t hk_prove_batch(hk_ctx* ctx, uint64_t pk_h, size_t K, const uin
             require_aligned16(c_affine, "hk_prove c");
             by_curve(ctx, [&] { prove_run<Bls12381>(ctx, pk, K, z, r, s, kappas, a_affine, b_affine, c_affine, inf); },
                      [&] { prove_run<Bn254>(ctx, pk, K, z, r, s, kappas, a_affine, b_affine, c_affine, inf); });
+            return;
+        }
+        if (memspace == HK_HOST_PINNED_ASYNC) {
+            HK_REQUIRE(inf, HK_ERR_INVALID, "inf is NULL");
+            const size_t zb = K * pk.m * 32, rb = K * 32, kb = K * (size_t)nk * 32;
+            async_streams(ctx);
+            const int slot = (int)(ctx->async_seq++ & 1);
+            char* dz = (char*)ctx->ws_zin[slot].ensure(zb + 2 * rb + kb + 64);
+            // upload on the copy stream once the previous user of this staging buffer has finished
+            HK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_in_free[slot], 0));
+            HK_CUDA(cudaMemcpyAsync(dz, z, zb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            HK_CUDA(cudaMemcpyAsync(dz + zb, r, rb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            HK_CUDA(cudaMemcpyAsync(dz + zb + rb, s, rb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (kb) HK_CUDA(cudaMemcpyAsync(dz + zb + 2 * rb, kappas, kb, cudaMemcpyHostToDevice, ctx->copy_stream));
+            HK_CUDA(cudaEventRecord(ctx->ev_h2d[slot], ctx->copy_stream));
+            HK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0));
+            const size_t out_bytes = K * (2 * p1 + p2 + 3);
+            char* d_out = (char*)ctx->ws_io[3].ensure(out_bytes + 64);
+            char* dA = d_out;
+            char* dB = dA + K * p1;
+            char* dC = dB + K * p2;
+            uint8_t* d_inf = (uint8_t*)(dC + K * p1);
+            const uint64_t* dzz = (const uint64_t*)dz;
+            const uint64_t* dr = (const uint64_t*)(dz + zb);
+            const uint64_t* ds = (const uint64_t*)(dz + zb + rb);
+            const uint64_t* dk = (const uint64_t*)(dz + zb + 2 * rb);
+            by_curve(ctx, [&] { prove_run<Bls12381>(ctx, pk, K, dzz, dr, ds, dk, dA, dB, dC, d_inf); },
+                     [&] { prove_run<Bn254>(ctx, pk, K, dzz, dr, ds, dk, dA, dB, dC, d_inf); });
+            HK_CUDA(cudaEventRecord(ctx->ev_in_free[slot], ctx->stream));
+            HK_CUDA(cudaMemcpyAsync(a_affine, dA, K * p1, cudaMemcpyDeviceToHost, ctx->stream));
+            HK_CUDA(cudaMemcpyAsync(b_affine, dB, K * p2, cudaMemcpyDeviceToHost, ctx->stream));
+            HK_CUDA(cudaMemcpyAsync(c_affine, dC, K * p1, cudaMemcpyDeviceToHost, ctx->stream));
+            HK_CUDA(cudaMemcpyAsync(inf, d_inf, K * 3, cudaMemcpyDeviceToHost, ctx->stream));
             return;
         }
         // host inputs -> device [z | r | s | kappas]; pageable inputs go through a pinned staging buffer

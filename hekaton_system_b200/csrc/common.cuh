@@ -212,6 +212,12 @@ struct hk_ctx {
     cudaStream_t qstream() const { return qap_stream ? qap_stream : stream; }
     void* pinned = nullptr;
     size_t pinned_cap = 0;
+    // asynchronous host-buffer calls (HK_HOST_PINNED_ASYNC): inputs are DMA'd on a copy stream into one of two
+    // device staging buffers, so the upload of call j+1 overlaps the kernels of call j
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {}, ev_in_free[2] = {};
+    uint64_t async_seq = 0;
+    hk::DevBuf ws_zin[2];
 
     // roofline profiling (hk_profile_*)
     bool prof_on = false;

@@ -38,6 +38,11 @@
  *     point pointers must be 16-byte aligned -- HK_ERR_INVALID otherwise),
  *     HK_HOST_PINNED (hk_prove_batch / hk_prove inputs only) = host memory that is already
  *     page-locked: inputs are DMA'd straight from the caller's buffers, no staging copy.
+ *     HK_HOST_PINNED_ASYNC (hk_commit_batch / hk_prove_batch) = inputs AND outputs are page-locked host
+ *     buffers; the call only enqueues (upload on a copy stream into one of two staging buffers, kernels,
+ *     download into the caller's output buffers) and returns.  Inputs must stay untouched and outputs are
+ *     valid only after hk_ctx_sync.  Several calls may be in flight on one context: the upload of the next
+ *     batch overlaps the kernels of the current one.
  *   - A context is bound to one GPU and one CUDA stream and is not thread-safe; use one
  *     context per host thread (the reference runs several proofs concurrently on separate
  *     threads, mpi-snark/src/bin/node.rs:773-793).  Calls with HK_HOST outputs
@@ -56,7 +61,7 @@ extern "C" {
 typedef struct hk_ctx hk_ctx;
 
 enum { HK_CURVE_BLS12_381 = 0, HK_CURVE_BN254 = 1 };
-enum { HK_HOST = 0, HK_DEVICE = 1, HK_HOST_PINNED = 2 };
+enum { HK_HOST = 0, HK_DEVICE = 1, HK_HOST_PINNED = 2, HK_HOST_PINNED_ASYNC = 3 };
 enum { HK_SCALAR_BIGINT = 0, HK_SCALAR_MONT = 1 };
 enum { HK_NTT_FORWARD = 0, HK_NTT_INVERSE = 1 };
 enum { HK_DOMAIN_PLAIN = 0, HK_DOMAIN_COSET_GENERATOR = 1 };

@@ -81,6 +81,48 @@ def test_prove_batch_matches_single(ctx):
         assert codec.g1_affine_from_limbs(c[k], cv)[0] == exp["C"]
 
 
+def test_async_host_calls_match_blocking(ctx):
+    """HK_HOST_PINNED_ASYNC: several commit / prove calls in flight on one context (uploads on the copy stream into
+    alternating staging buffers) give exactly the blocking calls' results once the context is synchronised."""
+    import random
+
+    import numpy as np
+    import torch
+    from hekaton_system_b200 import codec
+    cv = ctx.curve
+    K, L = 2, ctx.L
+    circ = og.synthetic_circuit(cv.name, 120, stage0_witnesses=5, seed=77)
+    td = og.sample_trapdoor(cv.name, 2, 78)
+    opk = og.generate_parameters(cv.name, circ, td)
+    pk = host.ProvingKey.from_key(ctx, opk, circ)
+    rng = random.Random(3)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).pin_memory().numpy().view(np.uint64)
+    pin8 = lambda *sh: torch.zeros(sh, dtype=torch.uint8).pin_memory().numpy()
+    z1 = codec.to_mont(circ.full_assignment(), cv.r, 4)
+    calls = []
+    for j in range(5):                      # 5 calls: both staging buffers are reused while earlier calls still run
+        rs = [rng.randrange(cv.r) for _ in range(K)]
+        ss = [rng.randrange(cv.r) for _ in range(K)]
+        ks = [rng.randrange(cv.r) for _ in range(K)]
+        inp = dict(z=pin(np.stack([z1] * K)), r=pin(codec.to_mont(rs, cv.r, 4)), s=pin(codec.to_mont(ss, cv.r, 4)),
+                   k=pin(codec.to_mont(ks, cv.r, 4).reshape(K, 1, 4)))
+        out = dict(a=pin(np.zeros((K, 2 * L), dtype=np.uint64)), b=pin(np.zeros((K, 4 * L), dtype=np.uint64)),
+                   c=pin(np.zeros((K, 2 * L), dtype=np.uint64)), inf=pin8(K, 3),
+                   com=pin(np.zeros((K, 2 * L), dtype=np.uint64)), cinf=pin8(K))
+        ctx.commit_batch_async(pk.handle, 0, inp["z"], inp["k"].reshape(K, 4), out["com"], out["cinf"])
+        ctx.prove_batch_async(pk.handle, inp["z"], inp["r"], inp["s"], inp["k"], out["a"], out["b"], out["c"], out["inf"])
+        calls.append((rs, ss, ks, inp, out))
+    ctx.sync()
+    for rs, ss, ks, inp, out in calls:
+        assert not out["inf"].any() and not out["cinf"].any()
+        for k in range(K):
+            exp = og.trapdoor_expected(opk, circ, td, rs[k], ss[k], [ks[k]])
+            assert codec.g1_affine_from_limbs(out["com"][k], cv)[0] == exp["D"][0]
+            assert codec.g1_affine_from_limbs(out["a"][k], cv)[0] == exp["A"]
+            assert codec.g2_affine_from_limbs(out["b"][k], cv)[0] == exp["B"]
+            assert codec.g1_affine_from_limbs(out["c"][k], cv)[0] == exp["C"]
+
+
 def test_circom_reference_fixture_end_to_end(ctx):
     """The circuit of the reference's own `.r1cs` fixture (circom-compat/src/lib.rs:548-600), loaded by
     hekaton_system_b200.circom, a satisfying witness, a trapdoor key -> device witness map, commit and
