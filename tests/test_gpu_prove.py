@@ -81,6 +81,37 @@ def test_prove_batch_matches_single(ctx):
         assert codec.g1_affine_from_limbs(c[k], cv)[0] == exp["C"]
 
 
+def test_seeded_rng_gives_byte_identical_proofs(ctx):
+    """north_star: "byte-identical proofs under the same seeded RNG".  The worker flow of the reference
+    (mpi-snark/src/worker.rs:62-66: kappa is the first Fr::rand of ChaCha12Rng::from_seed(com_seed);
+    prover.rs:28-29: r then s from the proving RNG) through the GPU CommitmentBuilder, against the oracle's restated
+    committer + prover fed from identical RNG instances: the ark-serialize encodings (compressed and uncompressed)
+    of the two proofs are the same bytes, and so are the commitments."""
+    from hekaton_system_b200 import rng as hrng
+    cv = ctx.curve
+    circ = og.synthetic_circuit(cv.name, 150, stage0_witnesses=9, seed=123)
+    td = og.sample_trapdoor(cv.name, 2, 124)
+    opk = og.generate_parameters(cv.name, circ, td)
+    pk = host.ProvingKey.from_key(ctx, opk, circ)
+    com_seed, prove_seed = bytes(range(32)), bytes([69] * 32)
+    # GPU path: draws happen inside commit / prove, in the reference's order
+    cb = host.CommitmentBuilder(host.StagedAssignment.from_circuit(circ, cv), pk)
+    com, kappa = cb.commit(rng=hrng.CurveRng(hrng.ChaChaRng(com_seed, 12), cv))
+    proof = cb.prove([com], [kappa], rng=hrng.CurveRng(hrng.ChaChaRng(prove_seed, 12), cv))
+    # oracle path with its own identically seeded RNGs
+    k2 = hrng.ChaChaRng(com_seed, 12).fr_rand(cv)
+    pr = hrng.ChaChaRng(prove_seed, 12)
+    r2, s2 = pr.fr_rand(cv), pr.fr_rand(cv)
+    com2 = og.commit(opk, circ, 0, k2)
+    A, Bp, C = og.prove(opk, circ, r2, s2, [k2])
+    ref = host.Proof(A, Bp, C, [com2])
+    assert kappa == k2
+    assert host.serialize_g1(com, cv) == host.serialize_g1(com2, cv)
+    for compress in (False, True):
+        assert proof.serialize(cv, compress) == ref.serialize(cv, compress)
+    assert len(proof.serialize(cv, True)) == 8 * cv.fq_limbs * 5 + 8      # A, B (2), C, one D + the Vec length
+
+
 def test_async_host_calls_match_blocking(ctx):
     """HK_HOST_PINNED_ASYNC: several commit / prove calls in flight on one context (uploads on the copy stream into
     alternating staging buffers) give exactly the blocking calls' results once the context is synchronised."""
