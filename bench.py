@@ -512,6 +512,12 @@ def main():
         mul_macs = 2 * n32 * n32 + n32                          # Montgomery multiply
         sqr_macs = n32 * (n32 + 1) // 2 + n32 * n32 + n32       # dedicated squaring (field_gen: *_sqr)
         macs_per_add = 8 * mul_macs + 2 * sqr_macs              # XYZZ mixed addition: 8M + 2S
+        # what this build executes: with the fused dual product (hk_build_flags & HK_BUILD_MUL2, BLS12-381 Fq only)
+        # Y3 = R (Q - X3) - Y1 PPP is ONE 3 N^2 + N pass instead of two multiplies: 6M + 2S + 1 dual = 2712
+        from hekaton_system_b200 import backend as hk_backend
+        flags = hk_backend.load_library().hk_build_flags()
+        dual = bool(flags & 1) and args.curve == "bls12_381"
+        exec_macs = (6 * mul_macs + 2 * sqr_macs + 3 * n32 * n32 + n32) if dual else macs_per_add
         ms_acc, n_acc, adds = prof_alone[0]
         ms_acc_p, n_acc_p, adds_p = prof[0]
         roof = None
@@ -526,10 +532,14 @@ def main():
                                     "(one 96-B affine base + one 8-B sorted pair)",
                     "launches": n_acc, "avg_launch_ms": ms_acc / n_acc, "units_per_launch": adds / n_acc,
                     "algorithmic_macs_per_unit": macs_per_add,
+                    "executed_macs_per_unit": exec_macs,
+                    "frac_executed": ach / imad_peak * exec_macs / macs_per_add,
                     "share_of_step": (ms_acc_p / ms_prof) if ms_prof else None,
                     "in_pipeline": {"frac": (adds_p * macs_per_add / (ms_acc_p * 1e-3) / imad_peak) if n_acc_p else None,
                                     "launches": n_acc_p, "avg_launch_ms": (ms_acc_p / n_acc_p) if n_acc_p else None},
-                    "note": "frac: CUDA events around every launch with the lanes of a batch serialised (each launch "
+                    "note": "frac: algorithmic MACs (8M + 2S per mixed addition, SURVEY 8d) / time / peak; frac_executed: "
+                            "the multiplies this build issues (fused dual product: one reduction fewer per addition) / "
+                            "time / peak = multiplier-pipe utilisation.  CUDA events around every launch with the lanes of a batch serialised (each launch "
                             "alone on the GPU, same kernels and inputs, right after the timed region); in_pipeline: the "
                             "same events while lanes and batches overlap, so a launch's duration includes the time it "
                             "shares the SMs with other kernels; share_of_step = summed in-pipeline launch time / wall time",

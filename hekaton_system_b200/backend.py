@@ -17,7 +17,8 @@ NTT_FORWARD, NTT_INVERSE = 0, 1
 OPT_BA_ROUNDS, OPT_BA_MIN_ITEMS = 1, 2
 DOMAIN_PLAIN, DOMAIN_COSET = 0, 1
 FIELD_FR, FIELD_FQ, FIELD_FQ2 = 0, 1, 2
-FOP_MUL, FOP_ADD, FOP_SUB, FOP_INV, FOP_TO_MONT, FOP_FROM_MONT, FOP_INV_GCD, FOP_SQR = range(8)
+(FOP_MUL, FOP_ADD, FOP_SUB, FOP_INV, FOP_TO_MONT, FOP_FROM_MONT, FOP_INV_GCD, FOP_SQR, FOP_MUL_KARA,
+ FOP_MULSUB2) = range(10)
 
 ERRORS = {0: "HK_OK", -1: "HK_ERR_INVALID", -2: "HK_ERR_CUDA", -3: "HK_ERR_NOMEM", -4: "HK_ERR_LENGTH",
           -5: "HK_ERR_HANDLE", -6: "HK_ERR_UNSUPPORTED", -7: "HK_ERR_NO_DEVICE"}
@@ -103,6 +104,8 @@ def load_library(path=None):
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = i32
+    lib.hk_build_flags.argtypes = []
+    lib.hk_build_flags.restype = C.c_uint32
     lib.hk_last_error_string.argtypes = [vp]
     lib.hk_last_error_string.restype = C.c_char_p
     lib.hk_launch_count.argtypes = [vp]

@@ -203,6 +203,8 @@ __global__ void k_field_op(const F* a, const F* b, F* out, size_t n, uint32_t op
         case HK_FOP_TO_MONT: r = x.to_mont(); break;
         case HK_FOP_INV_GCD: r = x.inverse_fast(); break;
         case HK_FOP_SQR: r = x.sqr(); break;
+        case HK_FOP_MUL_KARA: r = x.mul_kara(b[i]); break;
+        case HK_FOP_MULSUB2: r = F::mul_sub_mul_fused(x, b[i], b[i], x + b[i]); break;
         default: r = x.from_mont(); break;
     }
     out[i] = r;
@@ -884,8 +886,8 @@ HK_EXPORT int32_t hk_field_op(hk_ctx* ctx, uint32_t field, uint32_t op, const ui
                               uint64_t* out, size_t n) {
     return guarded(ctx, [&] {
         HK_REQUIRE(a && out, HK_ERR_INVALID, "NULL argument");
-        HK_REQUIRE(op <= HK_FOP_SQR, HK_ERR_INVALID, "bad op");
-        HK_REQUIRE(b || op >= HK_FOP_INV, HK_ERR_INVALID, "b is NULL");
+        HK_REQUIRE(op <= HK_FOP_MULSUB2, HK_ERR_INVALID, "bad op");
+        HK_REQUIRE(b || (op >= HK_FOP_INV && op <= HK_FOP_SQR), HK_ERR_INVALID, "b is NULL");
         if (n == 0) return;
         bool bls = ctx->curve == HK_CURVE_BLS12_381;
         if (field == HK_FIELD_FR) {

@@ -87,7 +87,7 @@ struct XYZZ {
         F PPP = P * PP;
         F Q = x * PP;
         F X3 = R.sqr() - PPP - Q.dbl();
-        F Y3 = R * (Q - X3) - y * PPP;
+        F Y3 = F::mul_sub_mul(R, Q - X3, y, PPP);
         x = X3;
         y = Y3;
         zz = zz * PP;
@@ -119,7 +119,7 @@ struct XYZZ {
         F PPP = P * PP;
         F Q = U1 * PP;
         F X3 = R.sqr() - PPP - Q.dbl();
-        F Y3 = R * (Q - X3) - S1 * PPP;
+        F Y3 = F::mul_sub_mul(R, Q - X3, S1, PPP);
         x = X3;
         y = Y3;
         zz = zz * q.zz * PP;

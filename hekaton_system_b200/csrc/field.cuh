@@ -17,7 +17,11 @@ namespace hk {
         static constexpr int N64 = NAME##_params::N64;                                        \
         static constexpr int BITS = NAME##_params::BITS;                                      \
         __device__ __forceinline__ static void mul(raw_t& r, const raw_t& a, const raw_t& b) { NAME##_mul(r, a, b); } \
+        __device__ __forceinline__ static void mulk(raw_t& r, const raw_t& a, const raw_t& b) { NAME##_mulk(r, a, b); } \
         __device__ __forceinline__ static void sqr(raw_t& r, const raw_t& a) { NAME##_sqr(r, a); }            \
+        static constexpr bool HAS_MUL2 = HK_HAS_MUL2_##NAME;                                  \
+        __device__ __forceinline__ static void mul2(raw_t& r, const raw_t& a, const raw_t& b, const raw_t& c, const raw_t& d) { NAME##_mul2(r, a, b, c, d); } \
+        __device__ __forceinline__ static void negp(raw_t& r, const raw_t& a) { NAME##_negp(r, a); }          \
         __device__ __forceinline__ static void add(raw_t& r, const raw_t& a, const raw_t& b) { NAME##_add(r, a, b); } \
         __device__ __forceinline__ static void sub(raw_t& r, const raw_t& a, const raw_t& b) { NAME##_sub(r, a, b); } \
         __device__ __forceinline__ static uint64_t mod(int i) { return NAME##_MOD[i]; }       \
@@ -36,7 +40,11 @@ HK_DEFINE_FIELD_TAG(bn254_fr)
 template <class Tag>
 __device__ __noinline__ typename Tag::raw_t fp_mul_call(typename Tag::raw_t a, typename Tag::raw_t b) {
     typename Tag::raw_t r;
+#ifdef HK_MUL_KARA
+    Tag::mulk(r, a, b);      // Karatsuba product + separate reduction (fewer wide multiplies, more ALU glue)
+#else
     Tag::mul(r, a, b);
+#endif
     return r;
 }
 
@@ -45,6 +53,15 @@ template <class Tag>
 __device__ __noinline__ typename Tag::raw_t fp_sqr_call(typename Tag::raw_t a) {
     typename Tag::raw_t r;
     Tag::sqr(r, a);
+    return r;
+}
+
+// Fused dual product (a*b + c*d with one reduction: 3N^2 + N wide multiplies instead of 4N^2 + 2N), same convention.
+template <class Tag>
+__device__ __noinline__ typename Tag::raw_t fp_mul2_call(typename Tag::raw_t a, typename Tag::raw_t b,
+                                                         typename Tag::raw_t c, typename Tag::raw_t d) {
+    typename Tag::raw_t r;
+    Tag::mul2(r, a, b, c, d);
     return r;
 }
 
@@ -93,7 +110,49 @@ struct Fp {
 #else
     __device__ __forceinline__ Fp sqr() const { Fp o; Tag::sqr(o.r, r); return o; }
 #endif
+    // Direct (inlined) entry points to the generated variants, independent of the build switches: test hooks.
+    __device__ __forceinline__ Fp mul_kara(const Fp& b) const { Fp o; Tag::mulk(o.r, r, b.r); return o; }
+    __device__ __forceinline__ static Fp mul_sub_mul_fused(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+        Fp nc, o;
+        Tag::negp(nc.r, c.r);
+        Tag::mul2(o.r, a.r, b.r, nc.r, d.r);
+        return o;
+    }
+    // a*b - c*d.  With -DHK_MUL2 (and a field with two spare bits above 3p) one fused dual product on (a, b, p - c, d).
+    __device__ __forceinline__ static Fp mul_sub_mul(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+#ifdef HK_MUL2
+        if constexpr (Tag::HAS_MUL2) {
+            Fp nc, o;
+            Tag::negp(nc.r, c.r);
+#ifdef HK_MUL_CALL
+            o.r = fp_mul2_call<Tag>(a.r, b.r, nc.r, d.r);
+#else
+            Tag::mul2(o.r, a.r, b.r, nc.r, d.r);
+#endif
+            return o;
+        } else
+#endif
+        return a * b - c * d;
+    }
+    // a*b + c*d, same switch
+    __device__ __forceinline__ static Fp mul_add_mul(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+#ifdef HK_MUL2
+        if constexpr (Tag::HAS_MUL2) {
+            Fp o;
+#ifdef HK_MUL_CALL
+            o.r = fp_mul2_call<Tag>(a.r, b.r, c.r, d.r);
+#else
+            Tag::mul2(o.r, a.r, b.r, c.r, d.r);
+#endif
+            return o;
+        } else
+#endif
+        return a * b + c * d;
+    }
     __device__ __forceinline__ Fp dbl() const { Fp o; Tag::add(o.r, r, r); return o; }
+    static constexpr bool HAS_MUL2 = Tag::HAS_MUL2;
+    // p - a, not reduced (p for a = 0): only as an operand of the fused dual product
+    __device__ __forceinline__ Fp neg_raw() const { Fp o; Tag::negp(o.r, r); return o; }
     __device__ __forceinline__ Fp neg() const { Fp z = zero(); Fp o; Tag::sub(o.r, z.r, r); return o; }
 
     // Montgomery <-> canonical
@@ -244,10 +303,33 @@ struct Fp2T {
     __device__ __forceinline__ Fp2T dbl() const { return {c0.dbl(), c1.dbl()}; }
     __device__ __forceinline__ Fp2T neg() const { return {c0.neg(), c1.neg()}; }
     __device__ __forceinline__ Fp2T operator*(const Fp2T& b) const {
+#if defined(HK_FP2_DUAL) && defined(HK_MUL2)
+        // two fused dual products (2 x (3N^2 + N) wide multiplies, no additions) instead of Karatsuba's three
+        // multiplies and five additions
+        if constexpr (F::HAS_MUL2) {
+            return {F::mul_sub_mul(c0, b.c0, c1, b.c1), F::mul_add_mul(c0, b.c1, c1, b.c0)};
+        }
+#endif
         F t0 = c0 * b.c0;
         F t1 = c1 * b.c1;
         F s = (c0 + c1) * (b.c0 + b.c1);
         return {t0 - t1, s - t0 - t1};
+    }
+    __device__ __forceinline__ static Fp2T mul_sub_mul(const Fp2T& a, const Fp2T& b, const Fp2T& c, const Fp2T& d) {
+        return a * b - c * d;
+    }
+    // test hooks (see Fp): the base-field variants under the same Karatsuba / dual-product composition
+    __device__ __forceinline__ Fp2T mul_kara(const Fp2T& b) const {
+        F t0 = c0.mul_kara(b.c0);
+        F t1 = c1.mul_kara(b.c1);
+        F s = (c0 + c1).mul_kara(b.c0 + b.c1);
+        return {t0 - t1, s - t0 - t1};
+    }
+    __device__ __forceinline__ static Fp2T mul_sub_mul_fused(const Fp2T& a, const Fp2T& b, const Fp2T& c, const Fp2T& d) {
+        // (a*b - c*d).c0 = a0 b0 - a1 b1 - (c0 d0 - c1 d1),  .c1 = a0 b1 + a1 b0 - (c0 d1 + c1 d0)
+        F r0 = F::mul_sub_mul_fused(a.c0, b.c0, a.c1, b.c1) - F::mul_sub_mul_fused(c.c0, d.c0, c.c1, d.c1);
+        F r1 = F::mul_sub_mul_fused(a.c0, b.c1, a.c1.neg(), b.c0) - F::mul_sub_mul_fused(c.c0, d.c1, c.c1.neg(), d.c0);
+        return {r0, r1};
     }
     __device__ __forceinline__ Fp2T sqr() const {
         F s = c0 + c1;

@@ -17,6 +17,12 @@
 // One copy of the Montgomery multiply per kernel instead of one per call site: measured +12 % on the
 // proof pipeline and -15 % on the G2 MSM (instruction-cache pressure).
 #define HK_MUL_CALL 1
+#ifndef HK_NO_MUL2
+#define HK_MUL2 1   // a*b - c*d as one fused dual product (field.cuh mul_sub_mul): -6 % on the bucket accumulation
+#endif
+#ifndef HK_NO_FP2_DUAL
+#define HK_FP2_DUAL 1   // Fq2 multiply = two fused dual products instead of Karatsuba's 3 multiplies + 5 additions
+#endif
 #include "prove.cuh"
 
 #include "ntt_impl.cuh"

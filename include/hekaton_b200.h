@@ -81,7 +81,9 @@ enum {
 enum { HK_FIELD_FR = 0, HK_FIELD_FQ = 1, HK_FIELD_FQ2 = 2 };
 enum { HK_FOP_MUL = 0, HK_FOP_ADD = 1, HK_FOP_SUB = 2, HK_FOP_INV = 3, HK_FOP_TO_MONT = 4, HK_FOP_FROM_MONT = 5,
        HK_FOP_INV_GCD = 6 /* binary-GCD inverse (the one affine normalisation uses) */,
-       HK_FOP_SQR = 7 /* dedicated Montgomery squaring (falls back to a*a where the field has no spare bits) */ };
+       HK_FOP_SQR = 7 /* dedicated Montgomery squaring (falls back to a*a where the field has no spare bits) */,
+       HK_FOP_MUL_KARA = 8 /* a*b through the Karatsuba-product / separate-reduction multiply */,
+       HK_FOP_MULSUB2 = 9 /* a*b - b*(a+b) through the fused dual product (two multiplies where the field lacks it) */ };
 
 /* ---- context ---------------------------------------------------------------------- */
 /* `stream`: a cudaStream_t to launch on (e.g. torch's current stream), or NULL to create one. */
@@ -104,6 +106,12 @@ const char* hk_last_error_string(hk_ctx* ctx);
 /* Limb counts for this context's curve (fq_limbs64 = 6 or 4; fr_limbs64 = 4). */
 int32_t hk_curve_info(hk_ctx* ctx, uint32_t* fq_limbs64, uint32_t* fr_limbs64, uint32_t* fr_bits,
                       uint32_t* two_adicity);
+/* Arithmetic variants compiled into the MSM kernels of this library (same results bit for bit):
+ *   HK_BUILD_MUL2      a*b - c*d of the point additions as one fused dual product (BLS12-381 Fq; default on)
+ *   HK_BUILD_MUL_KARA  Karatsuba-product multiply (-DHK_MUL_KARA; measured slower, off)
+ *   HK_BUILD_FP2_DUAL  Fq2 multiply as two dual products (-DHK_FP2_DUAL; off) */
+enum { HK_BUILD_MUL2 = 1, HK_BUILD_MUL_KARA = 2, HK_BUILD_FP2_DUAL = 4 };
+uint32_t hk_build_flags(void);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t hk_launch_count(hk_ctx* ctx);
 

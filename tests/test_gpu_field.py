@@ -50,6 +50,17 @@ def test_prime_field_ops(ctx, field):
     # binary-GCD inverse (ALU-pipe variant used by the affine normalisations): same values
     got = codec.limbs_to_ints(ctx.field_op(field, B.FOP_INV_GCD, codec.ints_to_limbs(am, L)))
     assert got == [(pow(x, -1, mod) * R % mod) if x % mod else 0 for x in a[:200]]
+    # Karatsuba-product multiply (half-width edge values: equal / zero / all-ones halves) and the fused dual product
+    # a*b - b*(a+b) (one reduction; operand p - b reaches p itself for b = 0)
+    half = 1 << (32 * L)
+    ke = [half - 1, half, (half - 1) * half % mod, half + 1, (half + 1) * (half - 1) % mod, mod - half]
+    ka = a + [x % mod for x in ke for _ in ke]
+    kb = b + [y % mod for _ in ke for y in ke]
+    KA, KB = codec.ints_to_limbs(ka, L), codec.ints_to_limbs(kb, L)
+    got = codec.limbs_to_ints(ctx.field_op(field, B.FOP_MUL_KARA, KA, KB))
+    assert got == [x * y * Rinv % mod for x, y in zip(ka, kb)]
+    got = codec.limbs_to_ints(ctx.field_op(field, B.FOP_MULSUB2, KA, KB))
+    assert got == [(x * y - y * ((x + y) % mod)) * Rinv % mod for x, y in zip(ka, kb)]
 
 
 def test_fq2_ops(ctx):
@@ -65,6 +76,11 @@ def test_fq2_ops(ctx):
     A, Bm = enc(a), enc(b)
     mul = lambda x, y: ((x[0] * y[0] - x[1] * y[1]) % p, (x[0] * y[1] + x[1] * y[0]) % p)
     assert dec(ctx.field_op(B.FIELD_FQ2, B.FOP_MUL, A, Bm)) == [mul(x, y) for x, y in zip(a, b)]
+    assert dec(ctx.field_op(B.FIELD_FQ2, B.FOP_MUL_KARA, A, Bm)) == [mul(x, y) for x, y in zip(a, b)]
+    sub2 = lambda u, v: ((u[0] - v[0]) % p, (u[1] - v[1]) % p)
+    add2 = lambda u, v: ((u[0] + v[0]) % p, (u[1] + v[1]) % p)
+    assert dec(ctx.field_op(B.FIELD_FQ2, B.FOP_MULSUB2, A, Bm)) == \
+        [sub2(mul(x, y), mul(y, add2(x, y))) for x, y in zip(a, b)]
     assert dec(ctx.field_op(B.FIELD_FQ2, B.FOP_ADD, A, Bm)) == [((x[0] + y[0]) % p, (x[1] + y[1]) % p) for x, y in zip(a, b)]
     assert dec(ctx.field_op(B.FIELD_FQ2, B.FOP_SUB, A, Bm)) == [((x[0] - y[0]) % p, (x[1] - y[1]) % p) for x, y in zip(a, b)]
     inv = dec(ctx.field_op(B.FIELD_FQ2, B.FOP_INV, A[:50]))

@@ -101,6 +101,19 @@ class Prog:
             elif op == "subc.u32":
                 v = val(srcs[0]) - val(srcs[1]) - cf
                 R[dst] = v & M32
+            elif op in ("add.cc.u32", "addc.cc.u32", "addc.u32"):
+                v = val(srcs[0]) + val(srcs[1]) + (cf if op.startswith("addc") else 0)
+                R[dst] = v & M32
+                if ".cc" in op:
+                    cf = v >> 32
+            elif op in ("sub.cc.u32", "subc.cc.u32"):
+                v = val(srcs[0]) - val(srcs[1]) - (cf if op.startswith("subc") else 0)
+                R[dst] = v & M32
+                cf = 1 if v < 0 else 0
+            elif op == "xor.b32":
+                R[dst] = (val(srcs[0]) ^ val(srcs[1])) & M32
+            elif op == "assert_le1":
+                assert val(srcs[0]) <= 1, "top limb of a Karatsuba middle term out of range"
             elif op == "unpack":          # mov.b64 {lo,hi}, src
                 lo, hi = dst
                 v = val(srcs[0])
@@ -151,7 +164,7 @@ class Prog:
         if self.preds:
             lines.append(".reg .pred " + ", ".join(self.preds) + ";")
         for op, dst, srcs in self.ins:
-            if op in ("assert_nc", "assert_lo0", "assert_hi0"):
+            if op.startswith("assert_"):
                 continue
             if op == "unpack":
                 lines.append(f"mov.b64 {{{o(dst[0])}, {o(dst[1])}}}, {o(srcs[0])};")
@@ -284,6 +297,327 @@ class FieldGen:
         P.emit("assert_nc", None)
         self._final_sub(P, res, outs)
         return P, outs, ain + bin_
+
+    def gen_mul_kara(self, variant=""):
+        """Montgomery product with one level of Karatsuba on the integer product and a separate reduction:
+            a = a0 + a1*B, b = b0 + b1*B, B = 2^(16N)          (H = N/2 limbs per half)
+            z0 = a0*b0, z2 = a1*b1, zm = |a0 - a1| * |b1 - b0|   three H x H products, H^2 wide multiplies each
+            z1 = z0 + z2 +- zm  (= a0*b1 + a1*b0)
+            T  = z0 + z1*B + z2*B^2
+        then N reduction rows (m_i = column_i * (-p^-1), T += m_i * p << 32i) on the lane scheme of gen_mul with the
+        low half of T preloaded into the even lanes; the high half of T is added to the surviving lanes at the end.
+        3(N/2)^2 + N^2 + N wide multiplies instead of 2N^2 + N (BLS12-381 Fq: 264 instead of 300); the glue
+        (differences, conditional negations, the three merges) is ~130 32-bit add/sub/xor on the ALU pipe, which the
+        multiplier-bound MSM kernels leave idle (IMAD.WIDE issues once per 4 cycles per scheduler).
+        No carry is dropped: all lanes are non-negative and their weighted sum V stays below 2^(32(i+N+1)+30)
+        after row i (T_lo < 2^(32N), sum m_k p 2^(32k) < 2^(32(i+1)) p), so the last lane of the odd chain
+        (i+N-1) and the carry lane (i+N) cannot overflow; the simulator asserts every dropped carry is zero."""
+        N, N2 = self.N, self.N2
+        assert N % 4 == 0
+        H = N // 2
+        P = Prog()
+        outs = [f"r{k}" for k in range(N2)]
+        ain = [f"a{k}" for k in range(N2)]
+        bin_ = [f"b{k}" for k in range(N2)]
+        a, b = [], []
+        for k in range(N2):
+            lo, hi = P.r32("al"), P.r32("ah")
+            P.emit("unpack", (lo, hi), ain[k])
+            a += [lo, hi]
+        for k in range(N2):
+            lo, hi = P.r32("bl"), P.r32("bh")
+            P.emit("unpack", (lo, hi), bin_[k])
+            b += [lo, hi]
+
+        def chain(L, cols, prods, carry_lane, first_addend=None):
+            carrying = False
+            for idx, (c, (u, v)) in enumerate(zip(cols, prods)):
+                t = P.r64("t")
+                if idx == 0 and first_addend is not None:
+                    x64 = P.r64("x")
+                    P.emit("pack", x64, first_addend, 0)
+                    P.emit("mad.wide.u32", t, u, v, x64)
+                else:
+                    P.emit("mul.wide.u32", t, u, v)
+                if c in L:
+                    P.emit("addc.cc.u64" if carrying else "add.cc.u64", L[c], L[c], t)
+                    carrying = True
+                else:
+                    if carrying:
+                        L[c] = P.r64("L")
+                        P.emit("addc.cc.u64", L[c], t, 0)
+                    else:
+                        L[c] = t
+            if carry_lane is None:
+                if carrying:
+                    P.emit("assert_nc", None)
+            elif carrying:
+                assert carry_lane not in L
+                L[carry_lane] = P.r64("L")
+                P.emit("addc.u64", L[carry_lane], 0, 0)
+
+        def half_product(u, v):
+            """u, v: H 32-bit registers each -> 2H 32-bit limbs of u*v."""
+            L = {}
+            ev = list(range(0, H, 2))
+            od = list(range(1, H, 2))
+            for i in range(H):
+                chain(L, [i + j for j in ev], [(u[j], v[i]) for j in ev], i + H)
+                chain(L, [i + j for j in od], [(u[j], v[i]) for j in od], None)
+            # merge the two lane families: limb c = even-family half + odd-family half + carry
+            e32, o32 = {}, {}
+            for c in sorted(L):
+                lo, hi = P.r32("pl"), P.r32("ph")
+                P.emit("unpack", (lo, hi), L[c])
+                fam = e32 if c % 2 == 0 else o32
+                fam[c] = lo
+                if c + 1 < 2 * H:
+                    fam[c + 1] = hi
+                else:
+                    P.emit("assert_hi0", None, hi)
+            z = []
+            started = False
+            for c in range(2 * H):
+                if c in e32 and c in o32:
+                    w = P.r32("z")
+                    P.emit("addc.cc.u32" if started else "add.cc.u32", w, e32[c], o32[c])
+                    started = True
+                elif started:
+                    w = P.r32("z")
+                    P.emit("addc.cc.u32", w, e32.get(c, o32.get(c, 0)), 0)
+                else:
+                    w = e32.get(c, o32.get(c))
+                z.append(w)
+            P.emit("assert_nc", None)
+            return z
+
+        def abs_diff(u, v):
+            """|u - v| over H limbs and the sign mask (0xffffffff when u < v)."""
+            d = [P.r32("d") for _ in range(H)]
+            for k in range(H):
+                P.emit("sub.cc.u32" if k == 0 else "subc.cc.u32", d[k], u[k], v[k])
+            mask = P.r32("sm")
+            P.emit("subc.u32", mask, 0, 0)
+            out = []
+            for k in range(H):
+                t = P.r32("dx")
+                P.emit("xor.b32", t, d[k], mask)
+                out.append(t)
+            res = [P.r32("ad") for _ in range(H)]
+            for k in range(H):
+                P.emit("sub.cc.u32" if k == 0 else "subc.cc.u32", res[k], out[k], mask)
+            return res, mask
+
+        a0, a1, b0, b1 = a[:H], a[H:], b[:H], b[H:]
+        if "mfirst" in variant:
+            da, sa = abs_diff(a0, a1)
+            db, sb = abs_diff(b1, b0)
+            zm = half_product(da, db)
+            z0 = half_product(a0, b0)
+            z2 = half_product(a1, b1)
+        else:
+            z0 = half_product(a0, b0)
+            z2 = half_product(a1, b1)
+            da, sa = abs_diff(a0, a1)
+            db, sb = abs_diff(b1, b0)
+            zm = half_product(da, db)
+        sm = P.r32("sg")
+        P.emit("xor.b32", sm, sa, sb)             # all ones: subtract zm
+        # S = z0 + z2 (2H + 1 limbs)
+        S = [P.r32("s") for _ in range(2 * H + 1)]
+        for k in range(2 * H):
+            P.emit("add.cc.u32" if k == 0 else "addc.cc.u32", S[k], z0[k], z2[k])
+        P.emit("addc.u32", S[2 * H], 0, 0)
+        # z1 = S + (zm ^ sm) + (sm & 1), sign-extended: two's complement subtraction when sm is all ones
+        zx = []
+        for k in range(2 * H):
+            t = P.r32("zx")
+            P.emit("xor.b32", t, zm[k], sm)
+            zx.append(t)
+        z1 = [P.r32("m") for _ in range(2 * H + 1)]
+        cg = P.r32("cg")
+        P.emit("add.cc.u32", cg, sm, sm)          # carry flag = (sm != 0)
+        for k in range(2 * H):
+            P.emit("addc.cc.u32", z1[k], S[k], zx[k])
+        P.emit("addc.u32", z1[2 * H], S[2 * H], sm)
+        P.emit("assert_le1", None, z1[2 * H])
+        # T = z0 + z1 << 32H + z2 << 64H   (4H = 2N limbs)
+        T = list(z0[:H])
+        first = True
+        for k in range(H, 4 * H):
+            base = z0[k] if k < 2 * H else z2[k - 2 * H]
+            add = z1[k - H] if k - H <= 2 * H else 0
+            w = P.r32("T")
+            P.emit("add.cc.u32" if first else "addc.cc.u32", w, base, add)
+            first = False
+            T.append(w)
+        cz = None
+        if "dep" in variant:
+            # the carry out of T is provably zero; feeding it to the first reduction digit keeps the scheduler from
+            # sinking the upper halves of the glue chains into the reduction (their carry predicates would stay live
+            # across it: seven predicate registers are not enough and ptxas starts spilling them through P2R)
+            cz = P.r32("cz")
+            P.emit("addc.u32", cz, 0, 0)
+            P.emit("assert_hi0", None, cz)
+        else:
+            P.emit("assert_nc", None)
+
+        # ---- reduction: low half of T preloaded in the even lanes ----
+        L = {}
+        for c in range(0, N, 2):
+            L[c] = P.r64("L")
+            P.emit("pack", L[c], T[c], T[c + 1])
+        x = None
+        ev = list(range(0, N, 2))
+        od = list(range(1, N, 2))
+        for i in range(N):
+            lo, hi = P.r32("lo"), P.r32("hi")
+            P.emit("unpack", (lo, hi), L[i])
+            m = P.r32("m")
+            if x is None:
+                if cz is not None:
+                    lz = P.r32("lz")
+                    P.emit("add.u32", lz, lo, cz)
+                    lo = lz
+                P.emit("mul.lo.u32", m, lo, self.m32)
+            else:
+                sx = P.r32("sx")
+                P.emit("add.u32", sx, lo, x)
+                P.emit("mul.lo.u32", m, sx, self.m32)
+            chain(L, [i + j for j in ev], [(m, self.pl[j]) for j in ev], i + N, first_addend=x)
+            chain(L, [i + j for j in od], [(m, self.pl[j]) for j in od], None)
+            P.emit("assert_lo0", None, L[i])
+            lo2, hi2 = P.r32("z"), P.r32("x")
+            P.emit("unpack", (lo2, hi2), L[i])
+            x = hi2
+            del L[i]
+        odd32 = {N: x}
+        for c in range(N + 1, 2 * N, 2):
+            if c in L:
+                lo, hi = P.r32("ol"), P.r32("oh")
+                P.emit("unpack", (lo, hi), L[c])
+                odd32[c] = lo
+                if c + 1 < 2 * N:
+                    odd32[c + 1] = hi
+                else:
+                    P.emit("assert_hi0", None, hi)
+        res = []
+        for k in range(N2):
+            c = N + 2 * k
+            o64 = P.r64("o")
+            P.emit("pack", o64, odd32.get(c, 0), odd32.get(c + 1, 0))
+            lane = L.get(c)
+            if lane is None:
+                lane = P.r64("L")
+                P.emit("mov.u64", lane, 0)
+            P.emit("add.cc.u64" if k == 0 else "addc.cc.u64", lane, lane, o64)
+            res.append(lane)
+        P.emit("assert_nc", None)
+        for k in range(N2):
+            th = P.r64("th")
+            P.emit("pack", th, T[N + 2 * k], T[N + 2 * k + 1])
+            P.emit("add.cc.u64" if k == 0 else "addc.cc.u64", res[k], res[k], th)
+        P.emit("assert_nc", None)
+        self._final_sub(P, res, outs)
+        return P, outs, ain + bin_
+
+    def gen_mul2(self):
+        """Fused dual product (a*b + c*d) * R^-1 mod p with ONE reduction: 3N^2 + N wide multiplies instead of
+        2(2N^2 + N) for two Montgomery products and an addition (BLS12-381 Fq: 444 instead of 600).  Row i adds
+        a*b_i and c*d_i to the lanes, then the usual reduction row.  Needs 3p < 2^(32N-1) so that the running
+        total a*(b_0..b_i) + c*(d_0..d_i) + sum m_k p 2^(32k) < 3p 2^(32(i+1)) keeps the top lane of a row
+        (i+N-1) below 2^63 and the carry lane (i+N) below 2^31; the result is < (2p^2 + Rp)/R < 2p.  Inputs may be
+        any values <= p (so a caller can pass p - x for a difference of products)."""
+        N, N2 = self.N, self.N2
+        assert 3 * self.p < (1 << (32 * N - 1))
+        P = Prog()
+        outs = [f"r{k}" for k in range(N2)]
+        names = ["a", "b", "c", "d"]
+        ins = [f"{nm}{k}" for nm in names for k in range(N2)]
+        limbs = {}
+        for nm in names:
+            v = []
+            for k in range(N2):
+                lo, hi = P.r32(nm + "l"), P.r32(nm + "h")
+                P.emit("unpack", (lo, hi), f"{nm}{k}")
+                v += [lo, hi]
+            limbs[nm] = v
+        a, b, c, d = (limbs[nm] for nm in names)
+        L = {}
+        x = None
+
+        def chain(cols, prods, carry_lane, first_addend=None):
+            carrying = False
+            for idx, (col, (u, v)) in enumerate(zip(cols, prods)):
+                t = P.r64("t")
+                if idx == 0 and first_addend is not None:
+                    x64 = P.r64("x")
+                    P.emit("pack", x64, first_addend, 0)
+                    P.emit("mad.wide.u32", t, u, v, x64)
+                else:
+                    P.emit("mul.wide.u32", t, u, v)
+                if col in L:
+                    P.emit("addc.cc.u64" if carrying else "add.cc.u64", L[col], L[col], t)
+                    carrying = True
+                else:
+                    if carrying:
+                        L[col] = P.r64("L")
+                        P.emit("addc.cc.u64", L[col], t, 0)
+                    else:
+                        L[col] = t
+            if carry_lane is None:
+                if carrying:
+                    P.emit("assert_nc", None)
+            elif carrying:
+                if carry_lane in L:
+                    P.emit("addc.cc.u64", L[carry_lane], L[carry_lane], 0)
+                    P.emit("assert_nc", None)
+                else:
+                    L[carry_lane] = P.r64("L")
+                    P.emit("addc.u64", L[carry_lane], 0, 0)
+
+        ev = list(range(0, N, 2))
+        od = list(range(1, N, 2))
+        for i in range(N):
+            chain([i + j for j in ev], [(a[j], b[i]) for j in ev], i + N, first_addend=x)
+            chain([i + j for j in od], [(a[j], b[i]) for j in od], None)
+            chain([i + j for j in ev], [(c[j], d[i]) for j in ev], i + N)
+            chain([i + j for j in od], [(c[j], d[i]) for j in od], None)
+            lo, hi = P.r32("lo"), P.r32("hi")
+            P.emit("unpack", (lo, hi), L[i])
+            m = P.r32("m")
+            P.emit("mul.lo.u32", m, lo, self.m32)
+            chain([i + j for j in ev], [(m, self.pl[j]) for j in ev], i + N)
+            chain([i + j for j in od], [(m, self.pl[j]) for j in od], None)
+            P.emit("assert_lo0", None, L[i])
+            lo2, hi2 = P.r32("z"), P.r32("x")
+            P.emit("unpack", (lo2, hi2), L[i])
+            x = hi2
+            del L[i]
+        odd32 = {N: x}
+        for col in range(N + 1, 2 * N, 2):
+            if col in L:
+                lo, hi = P.r32("ol"), P.r32("oh")
+                P.emit("unpack", (lo, hi), L[col])
+                odd32[col] = lo
+                if col + 1 < 2 * N:
+                    odd32[col + 1] = hi
+                else:
+                    P.emit("assert_hi0", None, hi)
+        res = []
+        for k in range(N2):
+            col = N + 2 * k
+            o64 = P.r64("o")
+            P.emit("pack", o64, odd32.get(col, 0), odd32.get(col + 1, 0))
+            lane = L.get(col)
+            if lane is None:
+                lane = P.r64("L")
+                P.emit("mov.u64", lane, 0)
+            P.emit("add.cc.u64" if k == 0 else "addc.cc.u64", lane, lane, o64)
+            res.append(lane)
+        P.emit("assert_nc", None)
+        self._final_sub(P, res, outs)
+        return P, outs, ins
 
     def gen_sqr(self):
         """Dedicated Montgomery squaring: every off-diagonal product a_i*a_k (i < k) is taken once against
@@ -435,6 +769,17 @@ class FieldGen:
             P.emit("add.cc.u64" if k == 0 else "addc.cc.u64", outs[k], d[k], pm)
         return P, outs, ain + bin_
 
+    def gen_negp(self):
+        """p - a without reduction (a <= p): the negated operand of gen_mul2."""
+        N2 = self.N2
+        P = Prog()
+        outs = [f"r{k}" for k in range(N2)]
+        ain = [f"a{k}" for k in range(N2)]
+        for k in range(N2):
+            P.emit("sub.cc.u64" if k == 0 else "subc.cc.u64", outs[k], self.p64[k], ain[k])
+        P.emit("assert_nc", None)
+        return P, outs, ain
+
     # ---------- emit C++ ----------
     def cpp_fn(self, fname, P, outs, ins, out_early_clobber=False):
         omap = {}
@@ -451,7 +796,7 @@ class FieldGen:
         cons = "=&l" if out_early_clobber else "=l"
         outc = ", ".join(f'"{cons}"(r.v[{i}])' for i in range(n2))
         nin = len(ins) // n2
-        names = ["a", "b"][:nin]
+        names = ["a", "b", "c", "d"][:nin]
         inc = ", ".join(f'"l"({nm}.v[{i}])' for nm in names for i in range(n2))
         args = ", ".join(f"const {self.name}_t& {nm}" for nm in names)
         # HK_MUL_CALL=1 emits the big multiplies as real functions (one copy of the ~7 KB body per kernel
@@ -512,12 +857,26 @@ def emit_header(path):
         for cname, val, doc in extra_constants().get(name, []):
             out.append(f"__device__ __constant__ const uint64_t {name}_{cname}[{n2}] = {c_array64(val, n2)};   // {doc}\n")
         out.append(f"#define HK_HAS_SQR_{name} {1 if fg.has_sqr else 0}\n")
-        gens = [("mul", fg.gen_mul), ("add", fg.gen_add), ("sub", fg.gen_sub)]
+        gens = [("mul", fg.gen_mul), ("mulk", lambda: fg.gen_mul_kara("dep")), ("add", fg.gen_add), ("sub", fg.gen_sub)]
         if fg.has_sqr:
             gens.append(("sqr", fg.gen_sqr))
         for fname, gen in gens:
             P, outs, ins = gen()
             out.append(fg.cpp_fn(fname, P, outs, ins))
+        has_mul2 = 3 * p < (1 << (32 * fg.N - 1))
+        out.append(f"#define HK_HAS_MUL2_{name} {1 if has_mul2 else 0}\n")
+        if has_mul2:
+            P, outs, ins = fg.gen_mul2()
+            out.append(fg.cpp_fn("mul2", P, outs, ins))
+            P, outs, ins = fg.gen_negp()
+            out.append(fg.cpp_fn("negp", P, outs, ins))
+        if not has_mul2:
+            out.append(f"// no fused dual product: 3p >= 2^{32 * fg.N - 1}\n"
+                       f"__device__ __forceinline__ void {name}_mul2({name}_t& r, const {name}_t& a, const {name}_t& b, "
+                       f"const {name}_t& c, const {name}_t& d) "
+                       f"{{ {name}_t t, u; {name}_mul(t, a, b); {name}_mul(u, c, d); {name}_add(r, t, u); }}\n"
+                       f"__device__ __forceinline__ void {name}_negp({name}_t& r, const {name}_t& a) "
+                       f"{{ {name}_t z = {{}}; {name}_sub(r, z, a); }}\n")
         if not fg.has_sqr:
             out.append(f"// no dedicated squaring: 3p >= 2^{32 * fg.N} (the carry invariants need two spare bits)\n"
                        f"__device__ __forceinline__ void {name}_sqr({name}_t& r, const {name}_t& a) "
@@ -565,6 +924,39 @@ def selftest(iters=200, seed=1):
                 assert got == x * x * Rinv % p, (name, "sqr", hex(x), hex(got))
             nsq = sum(1 for op, _, _ in P.ins if op in ("mul.wide.u32", "mad.wide.u32"))
             print(f"{name}: sqr ok ({nsq} wide multiplies)")
+        # Karatsuba product + separate reduction
+        P, outs, ins = fg.gen_mul_kara("dep")
+        half = 1 << (16 * fg.N)
+        kedge = edge + [(half - 1) % p, half % p, ((half - 1) * half) % p, (half + 1) % p]
+        for x, y in [(x, y) for x in kedge for y in kedge] + [(rng.randrange(p), rng.randrange(p)) for _ in range(iters)]:
+            env = {}
+            for k in range(n2):
+                env[f"a{k}"] = lanes64(x, n2)[k]
+                env[f"b{k}"] = lanes64(y, n2)[k]
+            Rr = P.run(env)
+            got = sum(Rr[o] << (64 * k) for k, o in enumerate(outs))
+            assert got == x * y * Rinv % p, (name, "mulk", hex(x), hex(y))
+        nk = sum(1 for op, _, _ in P.ins if op in ("mul.wide.u32", "mad.wide.u32"))
+        print(f"{name}: mulk ok ({nk} wide multiplies)")
+        # fused dual product (operands up to and including p)
+        if 3 * p < (1 << (32 * fg.N - 1)):
+            P, outs, ins = fg.gen_mul2()
+            Pn, outs_n, _ = fg.gen_negp()
+            e4 = [0, 1, p, p - 1, R % p, (p - 1) // 2]
+            quads = [(w, x, y, z) for w in e4 for x in e4 for y in e4 for z in e4]
+            quads += [tuple(rng.randrange(p + 1) for _ in range(4)) for _ in range(iters)]
+            for w, x, y, z in quads:
+                env = {}
+                for nm, v in zip("abcd", (w, x, y, z)):
+                    for k in range(n2):
+                        env[f"{nm}{k}"] = lanes64(v, n2)[k]
+                Rr = P.run(env)
+                got = sum(Rr[o] << (64 * k) for k, o in enumerate(outs))
+                assert got == (w * x + y * z) * Rinv % p, (name, "mul2", hex(w), hex(x), hex(y), hex(z))
+                Rn = Pn.run({f"a{k}": lanes64(w, n2)[k] for k in range(n2)})
+                assert sum(Rn[o] << (64 * k) for k, o in enumerate(outs_n)) == p - w
+            n2w = sum(1 for op, _, _ in P.ins if op in ("mul.wide.u32", "mad.wide.u32"))
+            print(f"{name}: mul2 ok ({n2w} wide multiplies)")
         nmul = sum(1 for op, _, _ in progs["mul"][0].ins if op in ("mul.wide.u32", "mad.wide.u32"))
         print(f"{name}: ok  ({len(cases)} cases; mul = {nmul} wide multiplies, "
               f"{len(progs['mul'][0].ins)} PTX instructions)")
