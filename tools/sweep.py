@@ -71,7 +71,9 @@ def main(argv=None):
     ap.add_argument("--g2-hi", type=int, default=22)
     ap.add_argument("--cpu-max", type=int, default=20, help="largest log size timed on the CPU (0 = none)")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--ops", default="msm_g1,msm_g2,ntt", help="comma-separated subset of msm_g1,msm_g2,ntt")
     args = ap.parse_args(argv)
+    ops = set(args.ops.split(","))
 
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -97,6 +99,8 @@ def main(argv=None):
 
     # ---------------------------------------------------------------- MSM
     for group in (1, 2):
+        if f"msm_g{group}" not in ops:
+            continue
         enc = codec.g1_affine_to_limbs if group == 1 else codec.g2_affine_to_limbs
         gen_pt = cv.g1 if group == 1 else cv.g2
         gen = enc([gen_pt], cv)[0]
@@ -160,7 +164,7 @@ def main(argv=None):
     # ---------------------------------------------------------------- NTT
     one = codec.to_mont([1], cv.r, 4)[0]
     fr_macs = 2 * 8 * 8 + 8
-    for lg in range(args.lo, args.hi + 1):
+    for lg in (range(args.lo, args.hi + 1) if "ntt" in ops else ()):
         N = 1 << lg
         a = rng.integers(0, 1 << 60, size=(N, 4), dtype=np.uint64)      # raw Montgomery residues < r
         d = torch.from_numpy(a.view(np.int64)).cuda().view(-1)
