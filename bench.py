@@ -63,9 +63,9 @@ def parse():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_msm_accum<G1> per mixed addition, from the committed
-# `ncu --set full` capture (profiles/r01e_accum_setfull_raw.csv: 3.388 GB read + 0.209 GB written by a launch of
+# `ncu --set full` capture (profiles/r01f_accum_setfull_raw.csv: 3.379 GB read + 0.196 GB written by a launch of
 # 2^20 x 16 = 16 777 216 additions)
-NCU_ACCUM_DRAM_BYTES_PER_ADD = (3.388190e9 + 0.208797e9) / 16777216
+NCU_ACCUM_DRAM_BYTES_PER_ADD = (3.379023e9 + 0.195592e9) / 16777216
 
 
 def peaks():
@@ -527,7 +527,7 @@ def main():
                     "unit": "T wide-MAC/s (32x32+64 IMAD.WIDE)", "frac": ach / imad_peak,
                     "traffic": NCU_ACCUM_DRAM_BYTES_PER_ADD * adds / n_acc,
                     "traffic_note": f"dram read+write bytes per launch = {NCU_ACCUM_DRAM_BYTES_PER_ADD:.0f} B per addition "
-                                    "(ncu --set full capture of this kernel, profiles/r01e_accum_setfull_raw.csv: 3.60 GB for a launch of "
+                                    "(ncu --set full capture of this kernel, profiles/r01f_accum_setfull_raw.csv: 3.57 GB for a launch of "
                                     "16.8 M additions) x this run's additions per launch; algorithmic = 104 B per addition "
                                     "(one 96-B affine base + one 8-B sorted pair)",
                     "launches": n_acc, "avg_launch_ms": ms_acc / n_acc, "units_per_launch": adds / n_acc,
