@@ -23,6 +23,15 @@ Algorithm (mont_mul, N 32-bit limbs, N even, p < 2^(32N-1)):
     now lo32(L[i]) == 0 ;  x_{i+1} = hi32(L[i])
   result = (columns N..2N-1) = even family + odd family, then one conditional subtract.
 Cost: 2N^2 + N wide multiplies (+ N low multiplies for m_i).
+
+Variants generated from the same lane scheme (each with its own carry-bound argument in the docstring and the same
+instruction-level verification):
+  gen_sqr       dedicated squaring, N(N+1)/2 + N^2 + N                      (fields with two spare top bits)
+  gen_mul2      fused dual product (a*b + c*d) R^-1 with one reduction, 3N^2 + N   (3p < 2^(32N-1): BLS12-381 Fq)
+  gen_negp      p - a, unreduced: the negated operand of gen_mul2
+  gen_mul_kara  Karatsuba product + separate reduction, 3(N/2)^2 + N^2 + N   (opt-in -DHK_MUL_KARA: measured slower,
+                see DESIGN.md 3.1)
+tools/kara_experiment.py + tools/sass_mix.sh / sass_split.py give the per-pipe SASS mix of a variant without a GPU.
 """
 import argparse
 import os
