@@ -8,6 +8,9 @@
 #ifndef HK_NO_FP2_DUAL
 #define HK_FP2_DUAL 1   // Fq2 multiply = two fused dual products instead of Karatsuba's 3 multiplies + 5 additions
 #endif
+#ifndef HK_NO_FP2_FUSED_CALL
+#define HK_FP2_FUSED_CALL 1   // whole Fq2 multiply / square as one call (field.cuh fp2_mul_call)
+#endif
 #include "msm_impl.cuh"
 namespace hk {
 template void msm_run<Bn254, 2>(hk_ctx*, const MsmBases&, size_t, size_t, const Scalar256*, size_t, bool, void*, size_t, int);
