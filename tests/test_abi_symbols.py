@@ -46,3 +46,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_default_build_uses_the_fused_dual_product():
+    """hk_build_flags is a pure query (no CUDA call): the shipped library must have the measured-faster arithmetic
+    variants on (fused dual product, Fq2 multiply through it) and the measured-slower Karatsuba multiply off."""
+    from hekaton_system_b200 import backend as B
+    if not os.path.exists(B.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    flags = B.load_library().hk_build_flags()
+    assert flags & 1, "HK_BUILD_MUL2 missing"
+    assert flags & 4, "HK_BUILD_FP2_DUAL missing"
+    assert not flags & 2, "HK_BUILD_MUL_KARA must stay off by default"
