@@ -954,6 +954,14 @@ def selftest(iters=200, seed=1):
             e4 = [0, 1, p, p - 1, R % p, (p - 1) // 2]
             quads = [(w, x, y, z) for w in e4 for x in e4 for y in e4 for z in e4]
             quads += [tuple(rng.randrange(p + 1) for _ in range(4)) for _ in range(iters)]
+            # adversarial carries: operands made of all-ones / zero / one limbs, clipped to <= p
+            sat = [p, p - 1, p - (1 << 32), p - (1 << 64) + 1]
+            for _ in range(40):
+                v = 0
+                for i in range(fg.N):
+                    v |= rng.choice([M32, M32, 0, 1, rng.getrandbits(32)]) << (32 * i)
+                sat.append(min(v & ((1 << p.bit_length()) - 1), p))
+            quads += [tuple(rng.choice(sat) for _ in range(4)) for _ in range(3 * iters)]
             for w, x, y, z in quads:
                 env = {}
                 for nm, v in zip("abcd", (w, x, y, z)):
