@@ -24,7 +24,8 @@ SHAPES = {
     # name: (constraints, portal ops in stage 0)        domain size
     "big-merkle-small": (60_000, 1),    # config 1: 1 SHA2 iter, 1 portal  -> N = 2^16
     "big-merkle": (200_000, 8),         # config 3: 4 SHA2 iters, 8 portals -> N = 2^18
-    "vm": (1_140_000, 776),             # config 5: 1024 cycles x 1114      -> N = 2^21
+    "vm": (1_140_000, 54_320),          # config 5: 1024 cycles x 1114 -> N = 2^21; stage 0 = 70 x 3104 = 217 280
+                                        # committed trace values (a 2^17.7-point commitment MSM)
     "vkd": (12_000, 4),                 # config 4: 32 Poseidon two-to-one hashes + exec-tree path -> N = 2^14
     "tiny": (500, 2),                   # tests / smoke
 }
@@ -188,25 +189,29 @@ def key_scalars(wl, seed=7):
     return td, ks
 
 
-def expected_exponents(wl, z, r_, s_, kappas):
-    """Discrete logs (w.r.t. G resp. H) of D_i, A, B, C from O(m) scalar arithmetic."""
+def expected_exponents(wl, z, r_, s_, kappas, cache=None):
+    """Discrete logs (w.r.t. G resp. H) of D_i, A, B, C from O(m) scalar arithmetic.
+    `cache` (a dict owned by the caller, one per assignment) keeps the O(m) inner products, which do not
+    depend on (r, s, kappa)."""
     r = wl.curve.r
     td, ks = wl.trapdoor, wl.key_scalars
     inv = lambda v: pow(v, -1, r)
     l = wl.l
-    a_tau = sum(zi * ai for zi, ai in zip(z, ks["a_g"])) % r
-    b_tau = sum(zi * bi for zi, bi in zip(z, ks["b_g"])) % r
-    c_tau = sum(zi * ci for zi, ci in zip(z, ks["c_col"])) % r
+    if cache is None:
+        cache = {}
+    if "a_tau" not in cache:
+        cache["a_tau"] = sum(zi * ai for zi, ai in zip(z, ks["a_g"])) % r
+        cache["b_tau"] = sum(zi * bi for zi, bi in zip(z, ks["b_g"])) % r
+        cache["c_tau"] = sum(zi * ci for zi, ci in zip(z, ks["c_col"])) % r
+        cache["stage"] = [sum(z[l + s0 + j] * x for j, x in enumerate(ck)) % r
+                          for ck, s0 in zip(ks["ck"], wl.stage_start[:-1])]
+    a_tau, b_tau, c_tau = cache["a_tau"], cache["b_tau"], cache["c_tau"]
     d_last = td["deltas"][-1]
     a_exp = (td["alpha"] + a_tau + r_ * d_last) % r
     b_exp = (td["beta"] + b_tau + s_ * d_last) % r
     h_tau = (a_tau * b_tau - c_tau) % r * inv(ks["zt"]) % r
-    ds = []
-    for i, kap in enumerate(kappas):
-        s0, e0 = wl.stage_start[i], wl.stage_start[i + 1]
-        ds.append((sum(z[l + s0 + j] * x for j, x in enumerate(ks["ck"][i])) + kap * d_last) % r)
-    sl, el = wl.stage_start[-2], wl.stage_start[-1]
-    l_exp = sum(z[l + sl + j] * x for j, x in enumerate(ks["ck"][-1])) % r
+    ds = [(cache["stage"][i] + kap * d_last) % r for i, kap in enumerate(kappas)]
+    l_exp = cache["stage"][-1]
     h_exp = h_tau * ks["zt"] % r * inv(d_last) % r
     c_exp = (s_ * a_exp + r_ * b_exp - r_ * s_ * d_last + l_exp + h_exp
              - sum(k * d for k, d in zip(kappas, td["deltas"]))) % r

@@ -408,6 +408,46 @@ int orc_field_mul(int curve, int field, const uint64_t* a, const uint64_t* b, ui
     return 0;
 }
 
+/* sum_i a_i * b_i mod r for canonical (non-Montgomery) 256-bit inputs (reduced mod r first); out canonical.
+ * The exact expected exponent of an MSM over bases k_i * G (tests: the check shares nothing with any MSM). */
+#define DOT_IMPL(NAME, FRP)                                                                                        \
+    static void NAME##_red(FRP##_t* x) { while (FRP##_geq_mod(x)) FRP##_sub_mod_raw(x); }                          \
+    static int NAME(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out, int threads) {                  \
+        init_all();                                                                                                \
+        if (threads < 1) threads = 1;                                                                              \
+        FRP##_t* part = (FRP##_t*)calloc((size_t)threads, sizeof(FRP##_t));                                        \
+        _Pragma("omp parallel num_threads(threads)")                                                               \
+        {                                                                                                          \
+            int t = 0, nt = 1;                                                                                     \
+            OMP_IDS(t, nt);                                                                                        \
+            FRP##_t acc; memset(&acc, 0, sizeof acc);                                                              \
+            for (size_t i = (size_t)t; i < n; i += (size_t)nt) {                                                   \
+                FRP##_t x, y, p;                                                                                   \
+                memcpy(&x, a + 4 * i, 32); memcpy(&y, b + 4 * i, 32);                                              \
+                NAME##_red(&x); NAME##_red(&y);                                                                    \
+                FRP##_to_mont(&x, &x);            /* xR */                                                         \
+                FRP##_mul(&p, &x, &y);            /* xR * y / R = xy */                                            \
+                FRP##_add(&acc, &acc, &p);                                                                         \
+            }                                                                                                      \
+            part[t] = acc;                                                                                         \
+        }                                                                                                          \
+        FRP##_t tot; memset(&tot, 0, sizeof tot);                                                                  \
+        for (int t = 0; t < threads; t++) FRP##_add(&tot, &tot, &part[t]);                                         \
+        memcpy(out, &tot, 32);                                                                                     \
+        free(part);                                                                                                \
+        return 0;                                                                                                  \
+    }
+#ifdef _OPENMP
+#define OMP_IDS(t, nt) do { t = omp_get_thread_num(); nt = omp_get_num_threads(); } while (0)
+#else
+#define OMP_IDS(t, nt) do { } while (0)
+#endif
+DOT_IMPL(orc_dot_bls, bls_fr)
+DOT_IMPL(orc_dot_bn, bn_fr)
+int orc_dot_fr(int curve, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out, int threads) {
+    return curve == 0 ? orc_dot_bls(a, b, n, out, threads) : orc_dot_bn(a, b, n, out, threads);
+}
+
 /* ---- whole-proof restatement (prover.rs:53-156 + committer.rs:106-114) -------------------------
  * One macro per curve keeps every group operation in the reference's order. */
 typedef struct {

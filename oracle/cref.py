@@ -159,3 +159,15 @@ class CpuProver:
                              _p(c), C.c_int(threads))
         assert rc == 0
         return a, b, c
+
+
+def dot_fr(curve_id, a, b, threads=0):
+    """sum_i a_i * b_i mod r for (n, 4) canonical limb arrays -> Python int."""
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    assert a.shape == b.shape and a.shape[1] == 4
+    out = np.zeros(4, dtype=np.uint64)
+    rc = lib().orc_dot_fr(C.c_int(curve_id), _p(a), _p(b), C.c_size_t(a.shape[0]), _p(out),
+                          C.c_int(threads or (os.cpu_count() or 1)))
+    assert rc == 0
+    return sum(int(out[i]) << (64 * i) for i in range(4))
