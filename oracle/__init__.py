@@ -17,8 +17,13 @@ What the oracle IS pinned against (tests/test_oracle_*.py):
   * public curve constants: the standard BLS12-381 / BN254 G1 and G2
     generators lie on their curves and have order r;
   * the algebraic properties the reference's tests check: setup -> commit ->
-    prove -> verify_proof accepts (pairing check restated in oracle/pairing.py
-    following verifier.rs:23-71);
+    prove -> verify_proof accepts, tampered proofs are rejected (reduced ate
+    pairing + verifier.rs:23-71 restated in oracle/pairing.py, itself pinned
+    by bilinearity / non-degeneracy / order-r on the standard generators:
+    tests/test_oracle_pairing.py);
+  * RFC 7539 / ECRYPT ChaCha block vectors and the zcash-format BLS12-381
+    generator encodings for the host-side RNG and serialisers
+    (tests/test_rng.py, tests/test_serialize.py);
   * an MSM/NTT-free trapdoor known-answer for whole proofs (cpgroth16.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl

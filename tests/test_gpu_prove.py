@@ -186,3 +186,25 @@ def test_circom_reference_fixture_end_to_end(ctx):
     proof = cb.prove([com], [kap], r=777, s=888)
     exp = og.trapdoor_expected(opk, circ, td, 777, 888, [4242])
     assert (com, proof.a, proof.b, proof.c) == (exp["D"][0], exp["A"], exp["B"], exp["C"])
+
+
+def test_gpu_proof_passes_pairing_verifier(ctx):
+    """The reference's only end-to-end acceptance check (cp-groth16/src/lib.rs:179,312): verify_proof on the
+    device-produced (A, B, C, D_0), through the pairing oracle (oracle/pairing.py, verifier.rs:23-71) -- a check on
+    real group elements that shares nothing with the trapdoor known answer."""
+    from oracle import pairing as pr
+    from oracle.ec import groups
+    cv = ctx.curve
+    circ = og.synthetic_circuit(cv.name, 200, stage0_witnesses=11, seed=501)
+    td = og.sample_trapdoor(cv.name, 2, 502)
+    opk = og.generate_parameters(cv.name, circ, td)
+    pk = host.ProvingKey.from_key(ctx, opk, circ)
+    cb = host.CommitmentBuilder(host.StagedAssignment.from_circuit(circ, cv), pk)
+    com, kap = cb.commit(kappa=0x5eed5eed5eed)
+    proof = cb.prove([com], [kap], r=0xfeedbeef0123, s=cv.r - 77)
+    pvk = pr.prepare_verifying_key(opk)
+    pub = circ.instance[1:]
+    assert pr.verify_proof(pvk, proof.a, proof.b, proof.c, proof.ds, pub)
+    G1 = groups(cv.name)[0]
+    assert not pr.verify_proof(pvk, proof.a, proof.b, G1.add(proof.c, G1.gen), proof.ds, pub)
+    assert not pr.verify_proof(pvk, proof.a, proof.b, proof.c, proof.ds, [(pub[0] + 1) % cv.r] + pub[1:])

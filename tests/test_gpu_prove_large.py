@@ -23,7 +23,7 @@ class _Assign:
 def test_full_size_proof_matches_trapdoor(ctx, shape):
     cv = ctx.curve
     if cv.name != "bls12_381" and shape == "big-merkle":
-        pytest.skip("full-size run is on the primary curve; BN254 is covered at 2^16")
+        pytest.skip("BN254 at full size: tests/test_gpu_configs.py::test_big_merkle_full_size_bn254_batch")
     wl = workload.make_workload(cv, shape, seed=2, num_assignments=1)
     td, _ = workload.key_scalars(wl, seed=5)
     pk = workload.build_device_key(ctx, wl)
@@ -40,6 +40,15 @@ def test_full_size_proof_matches_trapdoor(ctx, shape):
     assert proof.a == G1.mul(G, exp["A"])
     assert proof.b == G2.mul(H, exp["B"])
     assert proof.c == G1.mul(G, exp["C"])
+    if shape == "big-merkle-small":
+        # independent acceptance check at N = 2^16: verify_proof (verifier.rs:23-71) through the pairing oracle
+        from oracle import pairing as pr
+        from types import SimpleNamespace
+        ks = wl.key_scalars
+        vk = SimpleNamespace(curve=cv, alpha_g=G1.mul(G, ks["alpha"]), beta_h=G2.mul(H, ks["beta"]),
+                             gamma_h=G2.mul(H, td["gamma"]), deltas_h=[G2.mul(H, d) for d in td["deltas"]],
+                             gamma_abc_g=[G1.mul(G, x) for x in ks["gamma_abc"]])
+        assert pr.verify_proof(pr.prepare_verifying_key(vk), proof.a, proof.b, proof.c, [com], z[1:wl.l])
     # h[N-1] == 0 at full size (prover.rs:128-129) through the resident-matrix witness map
     import numpy as np
     N = 1 << wl.log_n
