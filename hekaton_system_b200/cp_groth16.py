@@ -26,11 +26,18 @@ from .backend import SCALAR_MONT
 
 
 # ---- ark-serialize 0.4 encodings (CanonicalSerialize) -----------------------------------------------------
-# Restated from the published crate (third-party, un-vendored): field elements are canonical
-# little-endian bytes (8 per limb); a short-Weierstrass affine point is x (|| y when uncompressed) with two
-# flag bits OR-ed into the most significant byte written last: 0x80 = "y is the larger of {y, -y}", 0x40 =
-# point at infinity (then x = y = 0); Fq2 = c0 || c1 and compares c1 first; Vec<T> = u64 LE length + items.
-# PINNING: unpinned (the reference has no serialized fixture and cannot be built here).
+# Restated from the published crates (third-party, un-vendored).
+# * BN254 (ark-bn254 0.4 uses ark-ec's generic short-Weierstrass impl): field elements are canonical
+#   little-endian bytes (8 per limb); a point is x (|| y when uncompressed) with two flag bits OR-ed into the
+#   most significant byte written last: 0x80 = "y is the larger of {y, -y}", 0x40 = point at infinity (then
+#   x = y = 0); Fq2 = c0 || c1.
+# * BLS12-381 (ark-bls12-381 0.4 overrides SWCurveConfig::{serialize,deserialize}_with_mode for G1 and G2 with
+#   the zcash / IETF pairing-friendly-curves encoding, curves/util.rs): field elements are BIG-endian, Fq2 is
+#   written c1 || c0, and three flag bits sit in the top of the FIRST byte: 0x80 = compressed, 0x40 = infinity,
+#   0x20 = y is the lexicographically larger root (set only for compressed, finite points).
+# Both orders compare Fq2 elements by c1 first, then c0.  Vec<T> = u64 LE length + items.
+# PINNING: the BLS12-381 encoders reproduce the published zcash serialisations of the G1 / G2 generators
+# (tests/test_serialize.py); the BN254 flag layout is restated from ark-serialize and has no external vector.
 def _y_is_negative_fq(y, p):
     return y > (p - y) % p
 
@@ -40,8 +47,29 @@ def _y_is_negative_fq2(y, p):
     return (y[1], y[0]) > (ny[1], ny[0])
 
 
+def _is_zcash(curve):
+    return curve.name == "bls12_381"
+
+
+def _zcash_point(coords, negative, nb, compress):
+    """coords: field elements in file order (x [, y]; Fq2 already as c1, c0) or None for infinity."""
+    b = bytearray(b"".join(c.to_bytes(nb, "big") for c in coords))
+    if compress:
+        b[0] |= 0x80
+        if negative:
+            b[0] |= 0x20
+    return bytes(b)
+
+
 def serialize_g1(P, curve, compress=False):
     nb = 8 * curve.fq_limbs
+    if _is_zcash(curve):
+        if P is None:
+            b = bytearray(nb if compress else 2 * nb)
+            b[0] |= 0x40 | (0x80 if compress else 0)
+            return bytes(b)
+        x, y = P
+        return _zcash_point([x] if compress else [x, y], _y_is_negative_fq(y, curve.p), nb, compress)
     if P is None:
         b = bytearray(nb if compress else 2 * nb)
         b[-1] |= 0x40
@@ -55,6 +83,14 @@ def serialize_g1(P, curve, compress=False):
 
 def serialize_g2(P, curve, compress=False):
     nb = 8 * curve.fq_limbs
+    if _is_zcash(curve):
+        if P is None:
+            b = bytearray(2 * nb if compress else 4 * nb)
+            b[0] |= 0x40 | (0x80 if compress else 0)
+            return bytes(b)
+        (x0, x1), (y0, y1) = P
+        return _zcash_point([x1, x0] if compress else [x1, x0, y1, y0], _y_is_negative_fq2((y0, y1), curve.p), nb,
+                            compress)
     if P is None:
         b = bytearray(2 * nb if compress else 4 * nb)
         b[-1] |= 0x40
@@ -76,8 +112,23 @@ def _deser_fq(buf, nb, last=False):
     return int.from_bytes(b, "little"), flags
 
 
+def _zcash_fields(buf, nb, count):
+    """-> (flags byte, [count big-endian field elements]) of an UNCOMPRESSED zcash-format point."""
+    if len(buf) < nb * count:
+        raise ValueError("point truncated")
+    flags = buf[0] & 0xE0
+    if flags & 0x80:
+        raise ValueError("compressed flag set on an uncompressed point")
+    first = bytes([buf[0] & 0x1F]) + bytes(buf[1:nb])
+    vals = [int.from_bytes(first, "big")] + [int.from_bytes(buf[i * nb:(i + 1) * nb], "big") for i in range(1, count)]
+    return flags, vals
+
+
 def deserialize_g1_uncompressed(buf, curve):
     nb = 8 * curve.fq_limbs
+    if _is_zcash(curve):
+        flags, (x, y) = _zcash_fields(buf, nb, 2)
+        return None if flags & 0x40 else (x, y)
     x, _ = _deser_fq(buf, nb)
     y, flags = _deser_fq(buf[nb:], nb, last=True)
     return None if flags & 0x40 else (x, y)
@@ -85,6 +136,9 @@ def deserialize_g1_uncompressed(buf, curve):
 
 def deserialize_g2_uncompressed(buf, curve):
     nb = 8 * curve.fq_limbs
+    if _is_zcash(curve):
+        flags, (x1, x0, y1, y0) = _zcash_fields(buf, nb, 4)
+        return None if flags & 0x40 else ((x0, x1), (y0, y1))
     x0, _ = _deser_fq(buf, nb)
     x1, _ = _deser_fq(buf[nb:], nb)
     y0, _ = _deser_fq(buf[2 * nb:], nb)

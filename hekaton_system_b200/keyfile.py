@@ -17,8 +17,11 @@ field order (ark-serialize 0.4: fields in declaration order, `usize` as u64 LE, 
     CommitterKey (data_structures.rs:107-114)
         last_delta_g: G1, deltas_abc_g: Vec<Vec<G1>>
 
-Uncompressed short-Weierstrass affine point: x || y, canonical little-endian field elements (Fq2 = c0 || c1),
-flags in the two top bits of the LAST byte (0x80: y is the larger of {y, -y}; 0x40: infinity, x = y = 0).
+Uncompressed affine point, BN254 (ark-ec generic impl): x || y, canonical little-endian field elements
+(Fq2 = c0 || c1), flags in the two top bits of the LAST byte (0x80: y is the larger of {y, -y}; 0x40: infinity,
+x = y = 0).  BLS12-381 (ark-bls12-381 0.4 overrides the point encoding with the zcash format): x || y, BIG-endian
+field elements, Fq2 = c1 || c0, flags in the top three bits of the FIRST byte (0x80 compressed -- never set in
+these files --, 0x40 infinity, 0x20 unused when uncompressed).  See cp_groth16.py for the encoders.
 
 Point vectors are decoded in bulk with numpy into canonical 64-bit limb arrays plus an infinity mask (a
 2^18-constraint key holds ~10^6 points); `to_device` converts them to Montgomery form on the GPU
@@ -135,9 +138,21 @@ class _Reader:
             raise ValueError("key file truncated")
         a = np.frombuffer(self.b, dtype=np.uint8, count=n * width, offset=self.o).reshape(n, width).copy()
         self.o += n * width
-        flags = a[:, -1] & 0xC0
-        a[:, -1] &= 0x3F
-        inf = ((flags & 0x40) != 0).astype(np.uint8)
+        if host._is_zcash(self.cv):
+            flags = a[:, 0] & 0xE0
+            if (flags & 0x80).any():
+                raise ValueError("compressed flag set in an uncompressed key file")
+            a[:, 0] &= 0x1F
+            inf = ((flags & 0x40) != 0).astype(np.uint8)
+            # big-endian field elements -> little-endian; G2 stores (c1, c0) pairs -> (c0, c1)
+            el = a.reshape(n, width // self.nb, self.nb)[:, :, ::-1]
+            if group == 2:
+                el = el.reshape(n, 2, 2, self.nb)[:, :, ::-1, :].reshape(n, 4, self.nb)
+            a = np.ascontiguousarray(el).reshape(n, width)
+        else:
+            flags = a[:, -1] & 0xC0
+            a[:, -1] &= 0x3F
+            inf = ((flags & 0x40) != 0).astype(np.uint8)
         limbs = a.view("<u8").reshape(n, width // 8)
         if inf.any():
             if limbs[inf != 0].any():

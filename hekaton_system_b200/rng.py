@@ -12,8 +12,9 @@ Restated from the published algorithms (third-party crates, not vendored in /roo
   * ark-ff 0.4 `impl Distribution<Fp<P, N>> for Standard`: N u64 limbs (little-endian) straight from
     `rng.gen::<u64>()`, the top `REPR_SHAVE_BITS` cleared, rejected if >= modulus, and the accepted limbs
     ARE the Montgomery representation (no conversion).
-PINNING: the ChaCha block function is checked against the RFC 7539 section 2.3.2 vector; the word/limb
-conventions above are unpinned (no Rust toolchain here) -- tests/test_rng.py says so.
+PINNING (tests/test_rng.py): the block function against RFC 7539 2.3.2, the 8/12/20-round variants against the
+ECRYPT zero-key vectors, the stream's word / block / counter order against rand_chacha's own
+`test_chacha_true_values_a`; the `Fr::rand` shave / reject rule is unpinned (no Rust toolchain here).
 """
 import struct
 
