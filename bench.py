@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--inflight", type=int, default=2,
                     help="batches in flight per GPU: step i runs on pipeline i %% inflight (own contexts, streams and "
                          "scratch), so the latency-bound tail of one batch overlaps the head of the next")
+    ap.add_argument("--opt", action="append", default=[],
+                    help="MSM tuning knob for A/B runs, name=value with name in waves|smin|fold|chunk|cap|sortb "
+                         "(hk_ctx_set_option; results never depend on them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the standalone MSM / NTT measurements")
     ap.add_argument("--sweep", action="store_true",
@@ -250,6 +253,13 @@ def main():
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
     ctx = Context(args.curve, device=local, stream=stream.cuda_stream)
+    if args.opt:
+        from hekaton_system_b200 import backend as _B
+        names = {"waves": _B.OPT_ACCUM_WAVES, "smin": _B.OPT_ACCUM_SEG_MIN, "fold": _B.OPT_FOLD_SEG,
+                 "chunk": _B.OPT_REDUCE_CHUNK, "cap": _B.OPT_GATHER_CAP, "sortb": _B.OPT_SORT_BLOCKS_PER_SM}
+        for kv in args.opt:
+            k_, v_ = kv.split("=")
+            ctx.set_option(names[k_], int(v_))         # forks inherit the settings
     nstreams = max(1, min(args.streams, args.batch))
     inflight = max(1, args.inflight)
     # pipelines: each has, per sub-batch, a proof context and a commitment context (forks of `ctx`: shared

@@ -292,23 +292,25 @@ static int32_t ctx_make_side(hk_ctx* ctx) {
     int least = 0, greatest = 0;
     if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return HK_ERR_CUDA;
     auto ev = [](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
-    for (int l = 1; l < hk_ctx::LANES; l++) {
+    for (int l = 0; l < hk_ctx::LANES; l++) {
+        if (!ev(&ctx->ev_sorted[l]) || !ev(&ctx->ev_ready[l]) || !ev(&ctx->ev_accum[l]) || !ev(&ctx->ev_lane_done[l]))
+            return HK_ERR_CUDA;
+        if (l == 0) continue;          // lane 0 is the caller's stream
         int bulk = greatest + l < least ? greatest + l : least;
         if (cudaStreamCreateWithPriority(&ctx->lane_ctl[l], cudaStreamNonBlocking, greatest) != cudaSuccess) return HK_ERR_CUDA;
         if (cudaStreamCreateWithPriority(&ctx->lane_bulk[l], cudaStreamNonBlocking, bulk) != cudaSuccess) return HK_ERR_CUDA;
-        if (!ev(&ctx->ev_sorted[l]) || !ev(&ctx->ev_accum[l]) || !ev(&ctx->ev_lane_done[l])) return HK_ERR_CUDA;
     }
     if (!ev(&ctx->ev_fork)) return HK_ERR_CUDA;
     return HK_OK;
 }
 static void ctx_free_side(hk_ctx* ctx) {
-    for (int l = 1; l < hk_ctx::LANES; l++) {
+    for (int l = 0; l < hk_ctx::LANES; l++) {
         for (cudaStream_t st : {ctx->lane_ctl[l], ctx->lane_bulk[l]})
             if (st) {
                 cudaStreamSynchronize(st);
                 cudaStreamDestroy(st);
             }
-        for (cudaEvent_t e : {ctx->ev_sorted[l], ctx->ev_accum[l], ctx->ev_lane_done[l]})
+        for (cudaEvent_t e : {ctx->ev_sorted[l], ctx->ev_ready[l], ctx->ev_accum[l], ctx->ev_lane_done[l]})
             if (e) cudaEventDestroy(e);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -331,8 +333,6 @@ HK_EXPORT int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx
     ctx->curve = curve;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->sh = std::make_shared<SharedState>();
-    if (const char* e = getenv("HK_BA_ROUNDS")) ctx->ba_rounds = atoi(e) < 0 ? 0 : (atoi(e) > 5 ? 5 : atoi(e));
-    if (const char* e = getenv("HK_BA_MIN")) ctx->ba_min_items = (size_t)atoll(e);
     if (cudaSetDevice(device) != cudaSuccess) {
         delete ctx;
         return HK_ERR_CUDA;
@@ -386,8 +386,12 @@ HK_EXPORT int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out) {
     ctx->curve = parent->curve;
     ctx->sm_count = parent->sm_count;
     ctx->sh = parent->sh;
-    ctx->ba_rounds = parent->ba_rounds;
-    ctx->ba_min_items = parent->ba_min_items;
+    ctx->opt_accum_waves = parent->opt_accum_waves;
+    ctx->opt_accum_smin = parent->opt_accum_smin;
+    ctx->opt_fold_seg = parent->opt_fold_seg;
+    ctx->opt_reduce_g = parent->opt_reduce_g;
+    ctx->opt_gather_cap = parent->opt_gather_cap;
+    ctx->opt_sort_blocks = parent->opt_sort_blocks;
     if (cudaSetDevice(ctx->device) != cudaSuccess) {
         delete ctx;
         return HK_ERR_CUDA;
@@ -413,11 +417,32 @@ HK_EXPORT int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out) {
 HK_EXPORT int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value) {
     return guarded(ctx, [&] {
         switch (option) {
-            case HK_OPT_BA_ROUNDS:
-                HK_REQUIRE(value <= 5, HK_ERR_INVALID, "HK_OPT_BA_ROUNDS must be 0..5");
-                ctx->ba_rounds = (int)value;
+            case HK_OPT_ACCUM_WAVES:
+                HK_REQUIRE(value <= 64, HK_ERR_INVALID, "HK_OPT_ACCUM_WAVES must be 0..64");
+                ctx->opt_accum_waves = (uint32_t)value;
                 break;
-            case HK_OPT_BA_MIN_ITEMS: ctx->ba_min_items = (size_t)value; break;
+            case HK_OPT_ACCUM_SEG_MIN:
+                HK_REQUIRE(value <= 4096, HK_ERR_INVALID, "HK_OPT_ACCUM_SEG_MIN must be 0..4096");
+                ctx->opt_accum_smin = (uint32_t)value;
+                break;
+            case HK_OPT_FOLD_SEG:
+                HK_REQUIRE(value == 0 || value == 4 || value == 8 || value == 16 || value == 32, HK_ERR_INVALID,
+                           "HK_OPT_FOLD_SEG must be 0, 4, 8, 16 or 32");
+                ctx->opt_fold_seg = (uint32_t)value;
+                break;
+            case HK_OPT_REDUCE_CHUNK:
+                HK_REQUIRE(value <= 65536 && (value & (value - 1)) == 0, HK_ERR_INVALID,
+                           "HK_OPT_REDUCE_CHUNK must be 0 or a power of two");
+                ctx->opt_reduce_g = (uint32_t)value;
+                break;
+            case HK_OPT_SORT_BLOCKS_PER_SM:
+                HK_REQUIRE(value <= 64, HK_ERR_INVALID, "HK_OPT_SORT_BLOCKS_PER_SM must be 0..64");
+                ctx->opt_sort_blocks = (uint32_t)value;
+                break;
+            case HK_OPT_GATHER_CAP:
+                HK_REQUIRE(value <= 4096, HK_ERR_INVALID, "HK_OPT_GATHER_CAP must be 0..4096");
+                ctx->opt_gather_cap = (uint32_t)value;
+                break;
             default: throw HkError{HK_ERR_INVALID, "unknown option"};
         }
     });

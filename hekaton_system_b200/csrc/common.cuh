@@ -122,6 +122,7 @@ struct BaseSet {
     void* tbl = nullptr;
     int tbl_c = 0, tbl_W = 0;
     uint8_t* skip = nullptr;   // 1 byte per point: base is the point at infinity (built with the table)
+    std::mutex tbl_mu;         // serialises table construction (forked contexts share base sets); tbl is published last
     BaseSet() = default;
     BaseSet(const BaseSet&) = delete;
     BaseSet& operator=(const BaseSet&) = delete;
@@ -142,6 +143,25 @@ struct MsmBases {
 };
 inline MsmBases msm_view(const BaseSet& b) { return MsmBases{b.d, b.n, b.tbl, b.tbl_c, b.tbl_W, b.skip}; }
 
+// Window geometry of one MSM.
+struct MsmPlan {
+    int c;       // window bits
+    int W;       // windows
+    uint32_t B;  // buckets per window = 2^(c-1)
+};
+
+// A key-sorted digit list produced by msm_sort (msm_impl.cuh); valid until the owning lane sorts again.
+struct MsmSorted {
+    MsmPlan pl{};
+    bool table = false;
+    size_t n = 0, K = 0, offset = 0, n_total = 0;
+    uint32_t Wred = 0, nsets = 0, item_stride = 0;
+    size_t nkeys = 0, max_items = 0;
+    const uint64_t* pairs = nullptr;     // key << 32 | table index << 1 | sign, key order
+    const uint32_t* d_count = nullptr;   // device: number of pairs
+    int lane = 0;                        // lane whose workspace holds the list (ev_sorted[lane] marks it ready)
+};
+
 struct ProfRec {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int id = 0;
@@ -153,9 +173,7 @@ struct ProfRec {
 // of the same proof batch can run concurrently.
 struct MsmWs {
     DevBuf scalars, hist, items, buckets, chunks, wsum, scan, misc;
-    // batch-affine pre-reduction rounds (msm_impl.cuh): ping-pong point / pair lists,
-    // per-thread denominator products and the scratch of their batched inversion
-    DevBuf ba_pts[2], ba_pairs[2], ba_tot, ba_head, ba_pre, ba_lvl;
+    DevBuf heads, state;       // gather step: (first, last) of every short run; device flags / counters
 };
 
 struct NttDomain;   // ntt.cu
@@ -188,7 +206,7 @@ struct hk_ctx {
     // slots as blocks retire and hide under whichever accumulation is running.
     static constexpr int LANES = 6;
     cudaStream_t lane_ctl[LANES] = {}, lane_bulk[LANES] = {};
-    cudaEvent_t ev_fork = nullptr, ev_sorted[LANES] = {}, ev_accum[LANES] = {}, ev_lane_done[LANES] = {};
+    cudaEvent_t ev_fork = nullptr, ev_sorted[LANES] = {}, ev_ready[LANES] = {}, ev_accum[LANES] = {}, ev_lane_done[LANES] = {};
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
@@ -201,10 +219,8 @@ struct hk_ctx {
     // serial_lanes (hk_profile_enable(ctx, 2)): every lane maps to the caller's stream, so kernels run one
     // at a time and the profiling events bracket each kernel alone (roofline measurements)
     bool serial_lanes = false;
-    // batch-affine pre-reduction rounds of the MSM (0 = off) and the list length from which they apply
-    // (0 = always); hk_ctx_set_option
-    int ba_rounds = 0;
-    size_t ba_min_items = size_t(1) << 20;
+    // MSM tuning knobs (hk_ctx_set_option; 0 = built-in default, see msm_accumulate)
+    uint32_t opt_accum_waves = 0, opt_accum_smin = 0, opt_fold_seg = 0, opt_reduce_g = 0, opt_gather_cap = 0, opt_sort_blocks = 0;
     cudaStream_t lane_stream(int lane) const { return !serial_lanes && lane > 0 && lane < LANES ? lane_ctl[lane] : stream; }
     cudaStream_t bulk_stream(int lane) const { return !serial_lanes && lane > 0 && lane < LANES ? lane_bulk[lane] : stream; }
     // stream used by the NTT / QAP kernels (normally the main stream; prove_run points it at the H lane)
@@ -298,6 +314,13 @@ inline void prof_end(hk_ctx* ctx, int idx, uint64_t static_units, const uint32_t
 }
 
 // ---- per-module entry points (implemented in the respective .cu files) -----------------
+// msm_sort / msm_accumulate: the two halves of msm_run, exposed so that one sorted list can feed several base
+// sets of the same geometry (prove.cu: B in G1 and in G2).
+template <class Curve>
+MsmSorted msm_sort(hk_ctx* ctx, const MsmBases& bases, size_t offset, size_t n, const Scalar256* d_scalars, size_t K,
+                   bool scalars_mont, size_t sc_stride, int lane);
+template <class Curve, int GROUP>
+void msm_accumulate(hk_ctx* ctx, const MsmSorted& sorted, const MsmBases& bases, void* d_out_jac, int lane);
 // msm: out[k] = sum_{i<n} scalars[k * sc_stride + i] * bases[offset + i] for k < K, in ONE pass (the
 // batch index is an extra bucket-set dimension).  Scalars are device pointers; out receives K
 // Jacobian points (device).  sc_stride = 0 means n.

@@ -15,6 +15,8 @@
 namespace hk {
 template void msm_run<Bls12381, 1>(hk_ctx*, const MsmBases&, size_t, size_t, const Scalar256*, size_t, bool, void*, size_t, int);
 template void bases_precompute<Bls12381, 1>(hk_ctx*, BaseSet&, double);
+template void msm_accumulate<Bls12381, 1>(hk_ctx*, const MsmSorted&, const MsmBases&, void*, int);
+template MsmSorted msm_sort<Bls12381>(hk_ctx*, const MsmBases&, size_t, size_t, const Scalar256*, size_t, bool, size_t, int);
 }
 
 // Which arithmetic variants this build's MSM kernels use (bench.py reports the executed multiply count from it).

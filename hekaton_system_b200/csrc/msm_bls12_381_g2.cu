@@ -15,4 +15,5 @@
 namespace hk {
 template void msm_run<Bls12381, 2>(hk_ctx*, const MsmBases&, size_t, size_t, const Scalar256*, size_t, bool, void*, size_t, int);
 template void bases_precompute<Bls12381, 2>(hk_ctx*, BaseSet&, double);
+template void msm_accumulate<Bls12381, 2>(hk_ctx*, const MsmSorted&, const MsmBases&, void*, int);
 }

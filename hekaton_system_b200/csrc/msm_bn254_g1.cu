@@ -15,4 +15,6 @@
 namespace hk {
 template void msm_run<Bn254, 1>(hk_ctx*, const MsmBases&, size_t, size_t, const Scalar256*, size_t, bool, void*, size_t, int);
 template void bases_precompute<Bn254, 1>(hk_ctx*, BaseSet&, double);
+template void msm_accumulate<Bn254, 1>(hk_ctx*, const MsmSorted&, const MsmBases&, void*, int);
+template MsmSorted msm_sort<Bn254>(hk_ctx*, const MsmBases&, size_t, size_t, const Scalar256*, size_t, bool, size_t, int);
 }

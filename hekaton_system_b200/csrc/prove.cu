@@ -414,6 +414,17 @@ std::shared_ptr<PkDev> pk_create(hk_ctx* ctx, const hk_pk_desc& d) {
     bases_precompute<Curve, 2>(ctx, pk->b2_ext, wd);
     for (auto& ck : pk->ck_ext) bases_precompute<Curve, 1>(ctx, *ck, wd);
     bases_precompute<Curve, 1>(ctx, *pk->h_g, 1.0);
+    // B in G1 and B in G2 take the same scalars: when the two base sets have the same table geometry and the same
+    // points at infinity (b_i(tau) = 0 in both groups -- true for every honestly generated key), one sorted digit
+    // list serves both accumulations
+    pk->share_b_sort = pk->b1_ext.tbl && pk->b2_ext.tbl && pk->b1_ext.tbl_c == pk->b2_ext.tbl_c &&
+                       pk->b1_ext.tbl_W == pk->b2_ext.tbl_W && pk->b1_ext.n == pk->b2_ext.n;
+    if (pk->share_b_sort) {
+        std::vector<uint8_t> s1(pk->b1_ext.n), s2(pk->b2_ext.n);
+        HK_CUDA(cudaMemcpy(s1.data(), pk->b1_ext.skip, s1.size(), cudaMemcpyDeviceToHost));
+        HK_CUDA(cudaMemcpy(s2.data(), pk->b2_ext.skip, s2.size(), cudaMemcpyDeviceToHost));
+        pk->share_b_sort = s1 == s2;
+    }
     return pk;
 }
 template std::shared_ptr<PkDev> pk_create<Bls12381>(hk_ctx*, const hk_pk_desc&);
@@ -494,7 +505,13 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     for (int ln = 1; ln < hk_ctx::LANES; ln++) HK_CUDA(cudaStreamWaitEvent(ctx->lane_stream(ln), ctx->ev_fork, 0));
     msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, Sr, K, false, jac + 0, 0, LA);
     HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LA], ctx->lane_stream(LA)));
-    msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, Ss, K, false, jac + K, 0, LB1);
+    MsmSorted sorted_s;
+    if (pk.share_b_sort) {
+        sorted_s = msm_sort<Curve>(ctx, msm_view(pk.b1_ext), 0, m + 2, Ss, K, false, 0, LB1);
+        msm_accumulate<Curve, 1>(ctx, sorted_s, msm_view(pk.b1_ext), jac + K, LB1);
+    } else {
+        msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, Ss, K, false, jac + K, 0, LB1);
+    }
     // s*A, r*B1 and A's normalisation, on B1's control stream once A is there too
     XYZZ<Fq>* sab = ctx->ws_io[2].as<XYZZ<Fq>>(2 * K);
     HK_CUDA(cudaStreamWaitEvent(ctx->lane_stream(LB1), ctx->ev_lane_done[LA], 0));
@@ -503,7 +520,10 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     HK_LAUNCH_CHECK(ctx);
     HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LB1], ctx->lane_stream(LB1)));
     // the G2 MSM + B2's normalisation
-    msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, Ss, K, false, jacB2, 0, LB2);
+    if (pk.share_b_sort)
+        msm_accumulate<Curve, 2>(ctx, sorted_s, msm_view(pk.b2_ext), jacB2, LB2);     // same scalars, same list
+    else
+        msm_run<Curve, 2>(ctx, msm_view(pk.b2_ext), 0, m + 2, Ss, K, false, jacB2, 0, LB2);
     k_prove_finish_b2<Curve><<<Ku, 32, 0, ctx->lane_stream(LB2)>>>(jacB2, reinterpret_cast<Affine<Fq2>*>(d_outB), d_inf);
     HK_LAUNCH_CHECK(ctx);
     HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LB2], ctx->lane_stream(LB2)));

@@ -15,6 +15,7 @@ struct PkDev {
     std::vector<std::unique_ptr<BaseSet>> ck_ext;   // per stage: [ck.., delta_last (, deltas_g[0..ns-2])]
     std::shared_ptr<BaseSet> h_g;                   // shared with the caller's h_g base set
     uint64_t h_g_handle = 0;
+    bool share_b_sort = false;                      // b1_ext / b2_ext agree in geometry and infinity pattern
 };
 
 template <class Curve>

@@ -95,11 +95,19 @@ int32_t hk_ctx_create(int device, uint32_t curve, void* stream, hk_ctx** out);
  * Handle-table access is mutex-protected; each context is still single-threaded. */
 int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out);
 int32_t hk_ctx_destroy(hk_ctx* ctx);
-/* Tuning knobs of a context (forks inherit them at fork time).
- *   HK_OPT_BA_ROUNDS     batch-affine pre-reduction rounds of the MSM bucket accumulation, 0..5 (default 0 = off;
- *                        same results)
- *   HK_OPT_BA_MIN_ITEMS  apply them only to MSMs whose digit list can reach this length (default 2^20; 0 = always) */
-enum { HK_OPT_BA_ROUNDS = 1, HK_OPT_BA_MIN_ITEMS = 2 };
+/* Tuning knobs of a context's MSM pipeline (forks inherit them at fork time; 0 restores the built-in default;
+ * results never depend on them -- DESIGN.md 3.2):
+ *   HK_OPT_ACCUM_WAVES    cap of the bucket-accumulation grid in waves of resident CTAs (default 0 = no cap: one
+ *                         thread per minimum segment); with a cap the per-thread segment length follows from the
+ *                         item count on the device
+ *   HK_OPT_ACCUM_SEG_MIN  smallest segment length (default 32; 8 for short standalone lists)
+ *   HK_OPT_FOLD_SEG       entries per thread in the partial-list fold levels: 4, 8, 16 or 32 (default 16 inside a
+ *                         proof batch, 4 standalone)
+ *   HK_OPT_REDUCE_CHUNK   buckets per thread in the bucket reduction (power of two)
+ *   HK_OPT_GATHER_CAP     longest run of partial sums (in list entries) merged by one thread (default 48)
+ *   HK_OPT_SORT_BLOCKS_PER_SM  cap of the digit-sort grids in CTAs per SM (default 0 = one thread per scalar) */
+enum { HK_OPT_ACCUM_WAVES = 1, HK_OPT_ACCUM_SEG_MIN = 2, HK_OPT_FOLD_SEG = 3, HK_OPT_REDUCE_CHUNK = 4, HK_OPT_GATHER_CAP = 5,
+       HK_OPT_SORT_BLOCKS_PER_SM = 6 };
 int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value);
 int32_t hk_ctx_sync(hk_ctx* ctx);
 const char* hk_last_error_string(hk_ctx* ctx);
@@ -256,9 +264,7 @@ int32_t hk_bench_field_mul(hk_ctx* ctx, uint32_t field, uint32_t threads, uint32
  *         includes the time it shares the GPU with others);
  * on = 2: additionally serialise the lanes of hk_commit* / hk_prove* onto the context stream, so that every
  *         launch is timed alone (same kernels, same inputs; the batch itself runs slower). */
-enum { HK_PROF_MSM_ACCUM_G1 = 0, HK_PROF_MSM_ACCUM_G2 = 1, HK_PROF_NTT_PASS = 2,
-       HK_PROF_MSM_BA_G1 = 3, HK_PROF_MSM_BA_G2 = 4 /* batch-affine round (prefix + inversion + apply); units = entries in */,
-       HK_PROF_COUNT = 5 };
+enum { HK_PROF_MSM_ACCUM_G1 = 0, HK_PROF_MSM_ACCUM_G2 = 1, HK_PROF_NTT_PASS = 2, HK_PROF_COUNT = 3 };
 int32_t hk_profile_enable(hk_ctx* ctx, int32_t on);
 int32_t hk_profile_reset(hk_ctx* ctx);
 int32_t hk_profile_read(hk_ctx* ctx, uint32_t kernel_id, double* total_ms, uint64_t* launches, uint64_t* units);

@@ -272,7 +272,7 @@ def prepare_inputs(pvk, public_inputs):
     G1 = groups(vk.curve)[0]
     g_ic = vk.gamma_abc_g[0]
     for x, base in zip(public_inputs, vk.gamma_abc_g[1:]):
-        g_ic = G1.add(g_ic, G1.mul(base, x % vk.curve.r))
+        g_ic = G1.add(g_ic, G1.mul(base, x % get_curve(vk.curve).r))
     return g_ic
 
 

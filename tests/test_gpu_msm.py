@@ -239,17 +239,23 @@ def test_scalar_mul_matches_oracle(ctx, group):
     assert dec(out, cv, oinf) == [None if p is None else G.mul(p, s) for p, s in zip(pts, pw)]
 
 
-@pytest.mark.parametrize("rounds", [1, 3])
-def test_batch_affine_rounds_give_identical_results(ctx, rounds):
-    """HK_OPT_BA_ROUNDS (off by default): the batch-affine pre-reduction must not change any result.  Forced on
-    for every MSM of a forked context and run over the cases that stress it: runs of every length 0..40 in one
-    bucket (odd leftovers, padding), P + P, P - P, bases at infinity, uniform and witness-like scalars, G1 / G2,
-    table and plain mode, a batch."""
+@pytest.mark.parametrize("opts", [
+    {B.OPT_GATHER_CAP: 2, B.OPT_FOLD_SEG: 4},                       # every run too long for the gather step -> fold levels
+    {B.OPT_GATHER_CAP: 3, B.OPT_FOLD_SEG: 16, B.OPT_ACCUM_SEG_MIN: 1},
+    {B.OPT_ACCUM_WAVES: 1, B.OPT_ACCUM_SEG_MIN: 2, B.OPT_GATHER_CAP: 4096},   # one wave, long gather walks
+    {B.OPT_ACCUM_SEG_MIN: 512, B.OPT_REDUCE_CHUNK: 16},             # a handful of threads own the whole list
+    {B.OPT_ACCUM_WAVES: 64, B.OPT_ACCUM_SEG_MIN: 3, B.OPT_FOLD_SEG: 8, B.OPT_REDUCE_CHUNK: 1},
+])
+def test_tuning_options_never_change_results(ctx, opts):
+    """hk_ctx_set_option: the accumulation geometry (waves, minimum segment), the gather cap and the fold /
+    reduction chunking only move work between kernels.  Forced to extreme values on a forked context and run over
+    the cases that stress the segment borders: runs of every length 0..40 in one bucket, P + P, P - P, bases at
+    infinity, uniform and witness-like scalars, G1 / G2, table and plain mode."""
     cv = ctx.curve
     f = ctx.fork()
-    f.set_option(B.OPT_BA_ROUNDS, rounds)
-    f.set_option(B.OPT_BA_MIN_ITEMS, 0)
-    rng = random.Random(900 + rounds)
+    for k, v in opts.items():
+        f.set_option(k, v)
+    rng = random.Random(900 + sum(opts.values()))
     try:
         for group in (1, 2):
             G = groups(cv.name)[group - 1]

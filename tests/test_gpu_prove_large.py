@@ -45,7 +45,7 @@ def test_full_size_proof_matches_trapdoor(ctx, shape):
         from oracle import pairing as pr
         from types import SimpleNamespace
         ks = wl.key_scalars
-        vk = SimpleNamespace(curve=cv, alpha_g=G1.mul(G, ks["alpha"]), beta_h=G2.mul(H, ks["beta"]),
+        vk = SimpleNamespace(curve=cv.name, alpha_g=G1.mul(G, ks["alpha"]), beta_h=G2.mul(H, ks["beta"]),
                              gamma_h=G2.mul(H, td["gamma"]), deltas_h=[G2.mul(H, d) for d in td["deltas"]],
                              gamma_abc_g=[G1.mul(G, x) for x in ks["gamma_abc"]])
         assert pr.verify_proof(pr.prepare_verifying_key(vk), proof.a, proof.b, proof.c, [com], z[1:wl.l])
