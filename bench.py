@@ -49,7 +49,7 @@ def parse():
                     help="batches in flight per GPU: step i runs on pipeline i %% inflight (own contexts, streams and "
                          "scratch), so the latency-bound tail of one batch overlaps the head of the next")
     ap.add_argument("--opt", action="append", default=[],
-                    help="MSM tuning knob for A/B runs, name=value with name in waves|smin|fold|chunk|cap|sortb "
+                    help="MSM tuning knob for A/B runs, name=value with name in waves|smin|fold|chunk|gsort "
                          "(hk_ctx_set_option; results never depend on them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the standalone MSM / NTT measurements")
@@ -256,7 +256,7 @@ def main():
     if args.opt:
         from hekaton_system_b200 import backend as _B
         names = {"waves": _B.OPT_ACCUM_WAVES, "smin": _B.OPT_ACCUM_SEG_MIN, "fold": _B.OPT_FOLD_SEG,
-                 "chunk": _B.OPT_REDUCE_CHUNK, "cap": _B.OPT_GATHER_CAP, "sortb": _B.OPT_SORT_BLOCKS_PER_SM}
+                 "chunk": _B.OPT_REDUCE_CHUNK, "gsort": _B.OPT_SORT_GLOBAL_ATOMICS}
         for kv in args.opt:
             k_, v_ = kv.split("=")
             ctx.set_option(names[k_], int(v_))         # forks inherit the settings
@@ -438,13 +438,14 @@ def main():
     torch.cuda.synchronize()
     if args.timeline:
         from torch.profiler import ProfilerActivity, profile
+        nrun = 3 * inflight                       # steady state: the middle third is what tools/timeline_stats.py reads
         if args.timeline_host:
             run_host(2 * inflight)
         with profile(activities=[ProfilerActivity.CUDA]) as tp:
             if args.timeline_host:
-                run_host(2 * inflight)
+                run_host(nrun)
             else:
-                run_device(inflight)
+                run_device(nrun)
             torch.cuda.synchronize()
         tmp = args.timeline + ".chrome.json"
         tp.export_chrome_trace(tmp)
@@ -454,9 +455,14 @@ def main():
         t0_ = min(e["ts"] for e in evs)
         sids = {s_: i for i, s_ in enumerate(sorted({e["args"].get("stream") for e in evs}))}
         with open(args.timeline, "w") as f:
-            f.write("# start_us dur_us stream kernel\n")
+            f.write(f"# {nrun} steps of {args.batch} proofs, {inflight} in flight\n")
+            f.write("# start_us dur_us stream grid block regs kernel\n")
             for e in sorted(evs, key=lambda e: e["ts"]):
-                f.write(f"{e['ts'] - t0_:10.1f} {e['dur']:9.1f} s{sids[e['args'].get('stream')]} {e['name'][:100]}\n")
+                a_ = e["args"]
+                g_ = "x".join(str(v) for v in a_.get("grid", [])) or "-"
+                b_ = "x".join(str(v) for v in a_.get("block", [])) or "-"
+                f.write(f"{e['ts'] - t0_:10.1f} {e['dur']:9.1f} s{sids[a_.get('stream')]} {g_} {b_} "
+                        f"{a_.get('registers per thread', '-')} {e['name'][:100]}\n")
         ctx.close()
         return 0
     sampler = ClockSampler(local) if rank == 0 else None

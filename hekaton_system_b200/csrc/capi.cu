@@ -390,8 +390,7 @@ HK_EXPORT int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out) {
     ctx->opt_accum_smin = parent->opt_accum_smin;
     ctx->opt_fold_seg = parent->opt_fold_seg;
     ctx->opt_reduce_g = parent->opt_reduce_g;
-    ctx->opt_gather_cap = parent->opt_gather_cap;
-    ctx->opt_sort_blocks = parent->opt_sort_blocks;
+    ctx->opt_sort_global = parent->opt_sort_global;
     if (cudaSetDevice(ctx->device) != cudaSuccess) {
         delete ctx;
         return HK_ERR_CUDA;
@@ -435,14 +434,7 @@ HK_EXPORT int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value
                            "HK_OPT_REDUCE_CHUNK must be 0 or a power of two");
                 ctx->opt_reduce_g = (uint32_t)value;
                 break;
-            case HK_OPT_SORT_BLOCKS_PER_SM:
-                HK_REQUIRE(value <= 64, HK_ERR_INVALID, "HK_OPT_SORT_BLOCKS_PER_SM must be 0..64");
-                ctx->opt_sort_blocks = (uint32_t)value;
-                break;
-            case HK_OPT_GATHER_CAP:
-                HK_REQUIRE(value <= 4096, HK_ERR_INVALID, "HK_OPT_GATHER_CAP must be 0..4096");
-                ctx->opt_gather_cap = (uint32_t)value;
-                break;
+            case HK_OPT_SORT_GLOBAL_ATOMICS: ctx->opt_sort_global = value ? 1u : 0u; break;
             default: throw HkError{HK_ERR_INVALID, "unknown option"};
         }
     });
@@ -477,7 +469,7 @@ HK_EXPORT int32_t hk_bases_upload_g2(hk_ctx* ctx, const void* p, const uint8_t* 
 }
 HK_EXPORT int32_t hk_bases_free(hk_ctx* ctx, uint64_t handle) {
     return guarded(ctx, [&] {
-        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        HK_CUDA(cudaDeviceSynchronize());      // forks may still be reading the buffers on their own streams
         std::lock_guard<std::mutex> lk(ctx->sh->mu);
         auto it = ctx->sh->bases.find(handle);
         HK_REQUIRE(it != ctx->sh->bases.end(), HK_ERR_HANDLE, "unknown base-set handle");
@@ -669,7 +661,7 @@ HK_EXPORT int32_t hk_r1cs_upload(hk_ctx* ctx, size_t n, size_t l, size_t nw, con
 }
 HK_EXPORT int32_t hk_r1cs_free(hk_ctx* ctx, uint64_t handle) {
     return guarded(ctx, [&] {
-        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        HK_CUDA(cudaDeviceSynchronize());      // forks may still be reading the buffers on their own streams
         std::lock_guard<std::mutex> lk(ctx->sh->mu);
         auto it = ctx->sh->r1cs.find(handle);
         HK_REQUIRE(it != ctx->sh->r1cs.end(), HK_ERR_HANDLE, "unknown r1cs handle");
@@ -718,7 +710,7 @@ HK_EXPORT int32_t hk_pk_create(hk_ctx* ctx, const hk_pk_desc* desc, uint64_t* pk
 }
 HK_EXPORT int32_t hk_pk_free(hk_ctx* ctx, uint64_t pk_handle) {
     return guarded(ctx, [&] {
-        HK_CUDA(cudaStreamSynchronize(ctx->stream));
+        HK_CUDA(cudaDeviceSynchronize());      // forks may still be reading the buffers on their own streams
         std::lock_guard<std::mutex> lk(ctx->sh->mu);
         auto it = ctx->sh->pks.find(pk_handle);
         HK_REQUIRE(it != ctx->sh->pks.end(), HK_ERR_HANDLE, "unknown pk handle");
@@ -788,7 +780,8 @@ HK_EXPORT int32_t hk_commit_batch(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, si
 HK_EXPORT int32_t hk_commit(hk_ctx* ctx, uint64_t pk_h, uint32_t stage, const uint64_t* z, const uint64_t* kappa,
                             uint32_t memspace, void* com_affine, uint8_t* com_inf) {
     uint8_t scratch = 0;
-    if (memspace == HK_DEVICE && !com_inf) return HK_ERR_INVALID;
+    // the flag is written asynchronously for HK_DEVICE / HK_HOST_PINNED_ASYNC: a stack scratch would dangle
+    if ((memspace == HK_DEVICE || memspace == HK_HOST_PINNED_ASYNC) && !com_inf) return HK_ERR_INVALID;
     return hk_commit_batch(ctx, pk_h, stage, 1, z, 0, kappa, memspace, com_affine, com_inf ? com_inf : &scratch);
 }
 
@@ -902,7 +895,8 @@ HK_EXPORT int32_t hk_prove(hk_ctx* ctx, uint64_t pk_h, const uint64_t* z, const 
                            const uint64_t* kappas, uint32_t memspace, void* a_affine, void* b_affine, void* c_affine,
                            uint8_t* inf) {
     uint8_t scratch[3];
-    if (memspace == HK_DEVICE && !inf) return HK_ERR_INVALID;
+    // the flags are written asynchronously for HK_DEVICE / HK_HOST_PINNED_ASYNC: a stack scratch would dangle
+    if ((memspace == HK_DEVICE || memspace == HK_HOST_PINNED_ASYNC) && !inf) return HK_ERR_INVALID;
     return hk_prove_batch(ctx, pk_h, 1, z, r, s, kappas, memspace, a_affine, b_affine, c_affine,
                           inf ? inf : (memspace == HK_DEVICE ? nullptr : scratch));
 }

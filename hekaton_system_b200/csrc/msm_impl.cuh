@@ -9,12 +9,11 @@
 //                   3. k_msm_scatter   counting sort: pair = key << 32 | point index << 1 | sign
 //   msm_accumulate  4. k_msm_accum     balanced segmented accumulation: every thread owns one segment of the
 //                                      key-sorted list (so skewed 0/1-heavy witness scalars cost the same as
-//                                      uniform ones).  The grid is a fixed number of waves of resident CTAs and
-//                                      the segment length follows from the item count ON THE DEVICE
-//                                      (S = max(S_min, ceil(count / threads))): long lists get long segments, so
-//                                      the number of partial sums (two per thread: the runs cut by the segment
-//                                      borders) stays a small multiple of the machine width instead of growing
-//                                      with the list.  Interior runs go straight to their bucket.
+//                                      uniform ones).  Interior runs go straight to their bucket, the two runs cut
+//                                      by the segment borders go to a partial list.  Default: 32 items per thread,
+//                                      as many CTAs as that takes (fine-grained CTAs balance the tail best);
+//                                      HK_OPT_ACCUM_WAVES caps the grid, then the segment length follows from the
+//                                      item count ON THE DEVICE (S = max(S_min, ceil(count / threads))).
 //                   5. k_msm_fold      the same scheme over the partial list (full XYZZ additions), level by level
 //                   6. k_msm_reduce_level / k_msm_tree_sum   sum_v v * B_v by a RECURSIVE chunked weighted sum:
 //                                      chunk t of G buckets gives acc_t = sum_j j B_(tG+j) and run_t = sum_j B_(tG+j);
@@ -183,6 +182,71 @@ static __global__ void k_msm_scatter(const Scalar256* sc, size_t n, size_t K, si
     }
 }
 
+// ---- counting sort with block-private histograms in shared memory ---------------------------------
+// With a window table all windows of a scalar vector share ONE bucket set, so a vector's whole key space is
+// B = 2^(c-1) counters: 16 KB for the assignment MSMs (c = 13), 128 KB for the H MSM (c = 16) -- it fits in the
+// 227 KB of shared memory of an SM.  Block (j, k) owns chunk j of vector k: it histograms its digits with
+// shared-memory atomics, publishes cnt[(k B + b) J + j], and after ONE exclusive scan over that array (key-major,
+// block-minor: the offsets of a key's items from block j follow those from block j - 1) it re-reads its chunk and
+// places every item with a shared-memory cursor.  No global atomic is issued at all; the global-atomic kernels above
+// remain for bucket sets that do not fit (no table: W B counters).
+// Window 0 aggregates equal digits of a warp first (match.any): witness vectors are mostly ones, whose single
+// non-zero digit would otherwise serialise a warp on one shared-memory word.
+template <bool SCATTER>
+__global__ void __launch_bounds__(1024)
+k_msm_sort_smem(const Scalar256* __restrict__ sc, size_t n, size_t sc_stride, int c, int W, uint32_t B, uint32_t J,
+                uint32_t chunk, uint32_t item_stride, const uint8_t* __restrict__ skip, uint32_t* cnt, uint64_t* pairs) {
+    extern __shared__ uint32_t sm_cnt[];
+    const uint32_t j = blockIdx.x, k = blockIdx.y;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t* mine = cnt + (size_t)k * B * J + j;              // stride J between consecutive buckets
+    for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) sm_cnt[b] = SCATTER ? mine[(size_t)b * J] : 0u;
+    __syncthreads();
+    const size_t lo = (size_t)j * chunk;
+    const size_t hi = lo + chunk < n ? lo + chunk : n;
+    const size_t span = hi > lo ? hi - lo : 0;
+    const size_t padded = (span + 31) & ~(size_t)31;           // whole warps take part in match.any
+    const uint32_t key_base = k * B;
+    for (size_t o = threadIdx.x; o < padded; o += blockDim.x) {
+        const size_t i = lo + o;
+        bool active = o < span;
+        uint64_t s[4] = {0, 0, 0, 0};
+        if (active && skip && skip[i]) active = false;          // base at infinity contributes nothing
+        if (active) {
+            const Scalar256* p = sc + (size_t)k * sc_stride + i;
+            s[0] = p->v[0], s[1] = p->v[1], s[2] = p->v[2], s[3] = p->v[3];
+            active = (s[0] | s[1] | s[2] | s[3]) != 0;
+        }
+        if (!__any_sync(0xffffffffu, active)) continue;
+        uint32_t carry = 0;
+        for (int w = 0; w < W; w++) {
+            const int d = active ? msm_digit(s, w, c, W, carry) : 0;
+            uint32_t pos = 0;
+            if (w == 0) {
+                const unsigned amask = __ballot_sync(0xffffffffu, d != 0);
+                if (d != 0) {
+                    const uint32_t b = (uint32_t)(abs(d) - 1);
+                    const unsigned peers = __match_any_sync(amask, b);
+                    const int leader = __ffs(peers) - 1;
+                    uint32_t pos0 = 0;
+                    if ((int)lane == leader) pos0 = atomicAdd(&sm_cnt[b], (uint32_t)__popc(peers));
+                    if (SCATTER) pos = __shfl_sync(peers, pos0, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+                }
+            } else if (d != 0) {
+                pos = atomicAdd(&sm_cnt[abs(d) - 1], 1u);
+            }
+            if (SCATTER && d != 0) {
+                const uint32_t item = (((uint32_t)w * item_stride + (uint32_t)i) << 1) | (d < 0 ? 1u : 0u);
+                pairs[pos] = ((uint64_t)(key_base + (uint32_t)(abs(d) - 1)) << 32) | item;
+            }
+        }
+    }
+    if (!SCATTER) {
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) mine[(size_t)b * J] = sm_cnt[b];
+    }
+}
+
 // ---- exclusive scan (u32), in place; total written to *total --------------------------------
 static constexpr int SCAN_TPB = 256;
 static constexpr int SCAN_IPT = 8;
@@ -318,14 +382,12 @@ k_msm_accum(const Affine<F>* __restrict__ bases, const uint64_t* __restrict__ pa
 
 // Level >= 1: same scheme over a list of XYZZ partials (full adds); empty slots skipped.
 // `final_level`: single thread range covers everything -> all runs are complete.
-// `d_need`: device flag written by k_msm_gather_classify -- 0 means the gather step has already merged every
-// run of the partial list into its bucket, and the whole level chain returns at once.
+// (A run that is cut by a high-order thread border stays split until the level whose segments swallow that border,
+// so the chain runs all its levels: log2 of the list length, each a handful of dependent additions.)
 template <class F, int S>
 __global__ void __launch_bounds__(128)
 k_msm_fold(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys, uint32_t n_in,
-           XYZZ<F>* buckets, XYZZ<F>* out, uint32_t* out_keys, uint32_t nthreads, int final_level,
-           const uint32_t* __restrict__ d_need) {
-    if (*d_need == 0) return;
+           XYZZ<F>* buckets, XYZZ<F>* out, uint32_t* out_keys, uint32_t nthreads, int final_level) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads) return;
     size_t lo = (size_t)t * S;
@@ -369,92 +431,6 @@ k_msm_fold(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys,
         out_keys[2 * (size_t)t] = k0;
         out_keys[2 * (size_t)t + 1] = k1;
     }
-}
-
-// ---- gather: short runs of the partial list go to their bucket in one step -----------------------
-// The partial list is in key order (thread order of the sorted item list).  A bucket whose run was cut by segment
-// borders owns a RUN of consecutive entries (empty slots in between).  For the usual scalar distributions every
-// run is a handful of entries, so instead of halving the whole list level by level (log2(list) dependent launches
-// of mostly idle threads) the runs of at most `cap` entries are summed by one thread each:
-//   k_msm_gather_classify  per entry: locate the run's first and last entry (bounded walks over the keys only);
-//                          a short run is marked consumed (out_keys = NONE) and its first entry appends
-//                          (first, last) to the head list; entries of longer runs keep their key and raise *d_need
-//   k_msm_gather_sum       one thread per head: bucket[key] = sum of the run
-// Only the runs that were too long (one bucket holding a large share of the list: witness vectors that are
-// mostly ones) continue through the k_msm_fold levels, which return immediately when *d_need stays 0.
-// state[0] = need-fold flag, state[1] = number of heads
-static __global__ void k_msm_gather_classify(const uint32_t* __restrict__ keys, uint32_t n_ub,
-                                             const uint32_t* __restrict__ d_count, uint32_t s_min, uint32_t nthreads0,
-                                             uint32_t cap, uint32_t* out_keys, uint2* heads, uint32_t* state) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ub) return;
-    // entries actually written by the accumulation: two per thread that had items
-    const uint32_t count = *d_count;
-    uint32_t S = (count + nthreads0 - 1) / nthreads0;
-    if (S < s_min) S = s_min;
-    const uint32_t n_act = 2u * ((count + S - 1) / S);
-    uint32_t k = i < n_act ? keys[i] : KEY_NONE;
-    if (k == KEY_NONE) {
-        out_keys[i] = KEY_NONE;
-        return;
-    }
-    // backward: first entry of the run (bounded)
-    uint32_t first = i;
-    bool open_lo = true;                       // boundary not seen yet
-    for (uint32_t st = 1; st <= cap; st++) {
-        if (st > i) {
-            open_lo = false;
-            break;
-        }
-        const uint32_t kj = keys[i - st];
-        if (kj == KEY_NONE) continue;
-        if (kj != k) {
-            open_lo = false;
-            break;
-        }
-        first = i - st;
-    }
-    uint32_t last = i;
-    bool open_hi = true;
-    for (uint32_t st = 1; st <= cap; st++) {
-        if (i + st >= n_act) {
-            open_hi = false;
-            break;
-        }
-        const uint32_t kj = keys[i + st];
-        if (kj == KEY_NONE) continue;
-        if (kj != k) {
-            open_hi = false;
-            break;
-        }
-        last = i + st;
-    }
-    const bool is_short = !open_lo && !open_hi && (last - first + 1) < cap;   // extent <= cap - 1: every entry of
-                                                                              // the run sees both borders within cap steps
-    if (is_short) {
-        out_keys[i] = KEY_NONE;
-        if (first == i) {
-            const uint32_t slot = atomicAdd(&state[1], 1u);
-            heads[slot] = make_uint2(first, last);
-        }
-    } else {
-        out_keys[i] = k;
-        if (state[0] == 0) atomicOr(&state[0], 1u);
-    }
-}
-
-template <class F>
-__global__ void __launch_bounds__(128)
-k_msm_gather_sum(const XYZZ<F>* __restrict__ part, const uint32_t* __restrict__ keys, const uint2* __restrict__ heads,
-                 const uint32_t* __restrict__ state, XYZZ<F>* buckets) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= state[1]) return;
-    const uint2 h = heads[t];
-    const uint32_t k = keys[h.x];
-    XYZZ<F> acc = part[h.x];
-    for (uint32_t j = h.x + 1; j <= h.y; j++)
-        if (keys[j] == k) acc.add(part[j]);
-    buckets[k] = acc;
 }
 
 // ---- bucket reduction ------------------------------------------------------------------------
@@ -619,22 +595,53 @@ MsmSorted msm_sort(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, con
         d_sc = conv;
         sc_stride = n;
     }
-    uint32_t* hist = ws.hist.as<uint32_t>(so.nkeys + 4);
-    uint32_t* d_count = hist + so.nkeys;     // total item count lives right after the histogram
     uint64_t* pairs = ws.items.as<uint64_t>(so.max_items + 2);
-    HK_CUDA(cudaMemsetAsync(hist, 0, (so.nkeys + 4) * sizeof(uint32_t), st));
     const uint8_t* skip = bv.skip ? bv.skip + offset : nullptr;
-    // sort grids: optionally capped (grid-stride) so that these memory- and atomic-bound kernels take only a slice
-    // of every SM and the bucket accumulations of other lanes keep most of the multiplier pipes
-    unsigned sort_blocks = ceil_div(n * K, 256);
-    if (ctx->opt_sort_blocks && sort_blocks > ctx->opt_sort_blocks * (unsigned)ctx->sm_count)
-        sort_blocks = ctx->opt_sort_blocks * (unsigned)ctx->sm_count;
-    k_msm_hist<<<sort_blocks, 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, so.Wred, per_window, skip, hist);
-    HK_LAUNCH_CHECK(ctx);
-    exclusive_scan_u32(ctx, ws, st, hist, so.nkeys, d_count);
-    k_msm_scatter<<<sort_blocks, 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, so.Wred, per_window,
-                                               so.item_stride, skip, hist, pairs);
-    HK_LAUNCH_CHECK(ctx);
+    // blocks per vector for the shared-memory sort: about two resident waves (one block per SM when the counters
+    // take more than half of the shared memory), never less than 1024 scalars per block
+    const size_t smem_bytes = (size_t)pl.B * sizeof(uint32_t);
+    uint32_t J = 0;
+    if (so.table && smem_bytes <= 160 * 1024 && !ctx->opt_sort_global) {
+        const uint32_t per_sm = smem_bytes > 100 * 1024 ? 1u : 2u;
+        uint64_t want = ((uint64_t)ctx->sm_count * per_sm * 2 + K - 1) / K;
+        const uint64_t most = (n + 1023) / 1024;
+        if (want > most) want = most;
+        if (want < 1) want = 1;
+        J = (uint32_t)want;
+        if ((uint64_t)so.nkeys * J >= (uint64_t(1) << 31)) J = 0;
+    }
+    uint32_t* d_count;
+    if (J) {
+        const uint32_t chunk = (uint32_t)((n + J - 1) / J);
+        const size_t ncnt = so.nkeys * J;
+        uint32_t* cnt = ws.hist.as<uint32_t>(ncnt + 4);
+        d_count = cnt + ncnt;
+        static bool attr_set[64] = {};     // opt in to > 48 KB of dynamic shared memory once per device
+        if (!attr_set[ctx->device & 63]) {
+            HK_CUDA(cudaFuncSetAttribute(k_msm_sort_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            HK_CUDA(cudaFuncSetAttribute(k_msm_sort_smem<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_set[ctx->device & 63] = true;
+        }
+        const dim3 grid(J, (unsigned)K);
+        k_msm_sort_smem<false><<<grid, 1024, smem_bytes, st>>>(d_sc, n, sc_stride, pl.c, pl.W, pl.B, J, chunk, so.item_stride,
+                                                              skip, cnt, pairs);
+        HK_LAUNCH_CHECK(ctx);
+        exclusive_scan_u32(ctx, ws, st, cnt, ncnt, d_count);
+        k_msm_sort_smem<true><<<grid, 1024, smem_bytes, st>>>(d_sc, n, sc_stride, pl.c, pl.W, pl.B, J, chunk, so.item_stride,
+                                                             skip, cnt, pairs);
+        HK_LAUNCH_CHECK(ctx);
+    } else {
+        uint32_t* hist = ws.hist.as<uint32_t>(so.nkeys + 4);
+        d_count = hist + so.nkeys;     // total item count lives right after the histogram
+        HK_CUDA(cudaMemsetAsync(hist, 0, (so.nkeys + 4) * sizeof(uint32_t), st));
+        const unsigned sort_blocks = ceil_div(n * K, 256);
+        k_msm_hist<<<sort_blocks, 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, so.Wred, per_window, skip, hist);
+        HK_LAUNCH_CHECK(ctx);
+        exclusive_scan_u32(ctx, ws, st, hist, so.nkeys, d_count);
+        k_msm_scatter<<<sort_blocks, 256, 0, st>>>(d_sc, n, K, sc_stride, pl.c, pl.W, pl.B, so.Wred, per_window,
+                                                   so.item_stride, skip, hist, pairs);
+        HK_LAUNCH_CHECK(ctx);
+    }
     HK_CUDA(cudaEventRecord(ctx->ev_sorted[lane], st));
     so.pairs = pairs;
     so.d_count = d_count;
@@ -689,11 +696,7 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     for (uint32_t v : lvl_in) part_total += v;
     XYZZ<F>* buckets = ws.buckets.as<XYZZ<F>>(nkeys);
     XYZZ<F>* partial = ws.chunks.as<XYZZ<F>>(part_total);
-    // keys: [level-0 keys as written by the accumulation | the fold levels' key lists, level 0 = gather output]
-    uint32_t* partial_keys = ws.misc.as<uint32_t>(part_total + 2 * (size_t)nthr0);
-    uint32_t* raw_keys = partial_keys + part_total;
-    uint2* heads = ws.heads.as<uint2>(2 * (size_t)nthr0);
-    uint32_t* state = ws.state.as<uint32_t>(4);
+    uint32_t* partial_keys = ws.misc.as<uint32_t>(part_total);
     // reduction geometry: short serial chunks, then a multi-block tree
     // standalone (lane 0): short chunks shorten the serial tail; inside a proof batch the larger grids of a
     // latency-bound kernel take SM slots from the accumulations, so the lanes keep long chunks
@@ -709,7 +712,6 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     XYZZ<F>* chunk_out = ws.wsum.as<XYZZ<F>>(tree_total + nsets);
 
     HK_CUDA(cudaMemsetAsync(buckets, 0, nkeys * sizeof(XYZZ<F>), st));
-    HK_CUDA(cudaMemsetAsync(state, 0, 4 * sizeof(uint32_t), st));
     // the accumulation needs the sorted list (possibly another lane's) and this lane's cleared buckets
     if (sb != st) {
         HK_CUDA(cudaEventRecord(ctx->ev_ready[lane], st));
@@ -718,20 +720,13 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     if (sb != ctx->lane_stream(so.lane)) HK_CUDA(cudaStreamWaitEvent(sb, ctx->ev_sorted[so.lane], 0));
     int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2, sb);
     k_msm_accum<F, MINB><<<ceil_div(nthr0, 128), 128, 0, sb>>>(d_bases, so.pairs, so.d_count, s_min, buckets, partial,
-                                                               raw_keys, nthr0);
+                                                               partial_keys, nthr0);
     HK_LAUNCH_CHECK(ctx);
     prof_end(ctx, pi, 0, so.d_count, sb);
     if (sb != st) {
         HK_CUDA(cudaEventRecord(ctx->ev_accum[lane], sb));
         HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_accum[lane], 0));
     }
-    // gather: runs of at most `cap` partial entries are merged by one thread each
-    const uint32_t cap = ctx->opt_gather_cap ? ctx->opt_gather_cap : 48u;
-    k_msm_gather_classify<<<ceil_div(2 * (size_t)nthr0, 256), 256, 0, st>>>(raw_keys, 2 * nthr0, so.d_count, s_min, nthr0, cap,
-                                                                           partial_keys, heads, state);
-    HK_LAUNCH_CHECK(ctx);
-    k_msm_gather_sum<F><<<ceil_div(2 * (size_t)nthr0, 128), 128, 0, st>>>(partial, raw_keys, heads, state, buckets);
-    HK_LAUNCH_CHECK(ctx);
     size_t off = 0;
     for (size_t l = 0; l < lvl_in.size(); l++) {
         uint32_t n_in = lvl_in[l];
@@ -741,10 +736,10 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
         uint32_t* in_keys = partial_keys + off;
         XYZZ<F>* out = partial + off + n_in;
         uint32_t* out_keys = partial_keys + off + n_in;
-        if (S1 == 8) k_msm_fold<F, 8><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level, state);
-        else if (S1 == 4) k_msm_fold<F, 4><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level, state);
-        else if (S1 == 32) k_msm_fold<F, 32><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level, state);
-        else k_msm_fold<F, 16><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level, state);
+        if (S1 == 8) k_msm_fold<F, 8><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
+        else if (S1 == 4) k_msm_fold<F, 4><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
+        else if (S1 == 32) k_msm_fold<F, 32><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
+        else k_msm_fold<F, 16><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
         HK_LAUNCH_CHECK(ctx);
         off += n_in;
     }

@@ -107,7 +107,11 @@ std::shared_ptr<R1csDev> r1cs_upload(hk_ctx* ctx, size_t n, size_t l, size_t nw,
     HK_REQUIRE(lg >= 1, HK_ERR_UNSUPPORTED, "r1cs: n + l must be >= 2");
     m->log_n = lg;
     for (int k = 0; k < 3; k++) {
+        HK_REQUIRE(ptr[k] && ptr[k][0] == 0, HK_ERR_INVALID, "r1cs: row_ptr must start at 0");
+        for (size_t i = 0; i < n; i++)
+            HK_REQUIRE(ptr[k][i] <= ptr[k][i + 1], HK_ERR_INVALID, "r1cs: row_ptr must be non-decreasing");
         size_t nnz = ptr[k][n];
+        HK_REQUIRE(nnz == 0 || (col[k] && val[k]), HK_ERR_INVALID, "r1cs: col / val missing for a non-empty matrix");
         m->nnz[k] = nnz;
         m->ptr[k] = m->b_ptr[k].as<uint32_t>(n + 1);
         m->col[k] = m->b_col[k].as<uint32_t>(nnz + 1);

@@ -104,10 +104,10 @@ int32_t hk_ctx_destroy(hk_ctx* ctx);
  *   HK_OPT_FOLD_SEG       entries per thread in the partial-list fold levels: 4, 8, 16 or 32 (default 16 inside a
  *                         proof batch, 4 standalone)
  *   HK_OPT_REDUCE_CHUNK   buckets per thread in the bucket reduction (power of two)
- *   HK_OPT_GATHER_CAP     longest run of partial sums (in list entries) merged by one thread (default 48)
- *   HK_OPT_SORT_BLOCKS_PER_SM  cap of the digit-sort grids in CTAs per SM (default 0 = one thread per scalar) */
-enum { HK_OPT_ACCUM_WAVES = 1, HK_OPT_ACCUM_SEG_MIN = 2, HK_OPT_FOLD_SEG = 3, HK_OPT_REDUCE_CHUNK = 4, HK_OPT_GATHER_CAP = 5,
-       HK_OPT_SORT_BLOCKS_PER_SM = 6 };
+ *   HK_OPT_SORT_GLOBAL_ATOMICS  1 = always sort the digits with the global-atomic kernels (default 0: base sets with a
+ *                         window table use block-private shared-memory histograms) */
+enum { HK_OPT_ACCUM_WAVES = 1, HK_OPT_ACCUM_SEG_MIN = 2, HK_OPT_FOLD_SEG = 3, HK_OPT_REDUCE_CHUNK = 4,
+       HK_OPT_SORT_GLOBAL_ATOMICS = 5 };
 int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value);
 int32_t hk_ctx_sync(hk_ctx* ctx);
 const char* hk_last_error_string(hk_ctx* ctx);

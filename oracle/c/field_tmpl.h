@@ -74,8 +74,17 @@ static inline void F(neg)(F(t) * r, const F(t) * a) {
     F(t) z; memset(&z, 0, sizeof z);
     F(sub)(r, &z, a);
 }
-/* CIOS Montgomery product (fully unrolled; branch-free final subtraction) */
+/* Montgomery product.  On x86-64 with BMI2 + ADX: the MULX / ADCX / ADOX routine of mont_asm.h (the instruction
+ * mix of ark-ff's `asm` feature, which the reference enables by default); otherwise portable CIOS (fully unrolled;
+ * branch-free final subtraction). */
 static inline __attribute__((always_inline)) void F(mul)(F(t) * r, const F(t) * a, const F(t) * b) {
+#ifdef ORC_HAVE_MONT_ASM
+    if (g_orc_use_asm) {
+        if (NL == 6) orc_mont_mul_asm_6(r->v, a->v, b->v, F(MOD).v, F(INV));
+        else orc_mont_mul_asm_4(r->v, a->v, b->v, F(MOD).v, F(INV));
+        return;
+    }
+#endif
     uint64_t t[NL + 2] = {0};
 #pragma GCC unroll 8
     for (int i = 0; i < NL; i++) {

@@ -17,9 +17,13 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include "mont_asm.h"
+/* 1 when the MULX/ADCX/ADOX multiplication may be used (decided once in init_all; ORC_NO_ASM=1 disables it) */
+static int g_orc_use_asm = 0;
 
 /* ---- arkworks window rule and signed-digit recoding ------------------------------------------ */
 static int ark_log2_ceil(size_t a) { int l = 0; while (((size_t)1 << l) < a) l++; return l; }
@@ -122,6 +126,10 @@ static const uint64_t BN_R[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0
 static int g_init = 0;
 static void init_all(void) {
     if (g_init) return;
+#if defined(ORC_HAVE_MONT_ASM)
+    __builtin_cpu_init();
+    g_orc_use_asm = __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("adx") && !getenv("ORC_NO_ASM");
+#endif
     bls_fq_init(BLS_P);
     bls_fr_init(BLS_R);
     bn_fq_init(BN_P);
@@ -446,6 +454,104 @@ DOT_IMPL(orc_dot_bls, bls_fr)
 DOT_IMPL(orc_dot_bn, bn_fr)
 int orc_dot_fr(int curve, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out, int threads) {
     return curve == 0 ? orc_dot_bls(a, b, n, out, threads) : orc_dot_bn(a, b, n, out, threads);
+}
+
+/* ---- baseline helpers ---------------------------------------------------------------------------- */
+int orc_uses_asm(void) { init_all(); return g_orc_use_asm; }
+
+/* ns per Montgomery multiplication, single thread, dependent chain; field 0 = Fr, 1 = Fq.  Printed beside the CPU
+ * baseline so that the reader can compare with ark-ff's published figures. */
+double orc_bench_field_mul(int curve, int field, long iters) {
+    init_all();
+    struct timespec t0, t1;
+    volatile uint64_t sink = 0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (field == 1 && curve == 0) {
+        bls_fq_t a = bls_fq_R2, b = bls_fq_R2; b.v[0] ^= 0x1234567;
+        for (long i = 0; i < iters; i++) bls_fq_mul(&a, &a, &b);
+        sink = a.v[0];
+    } else if (field == 1) {
+        bn_fq_t a = bn_fq_R2, b = bn_fq_R2; b.v[0] ^= 0x1234567;
+        for (long i = 0; i < iters; i++) bn_fq_mul(&a, &a, &b);
+        sink = a.v[0];
+    } else if (curve == 0) {
+        bls_fr_t a = bls_fr_R2, b = bls_fr_R2; b.v[0] ^= 0x1234567;
+        for (long i = 0; i < iters; i++) bls_fr_mul(&a, &a, &b);
+        sink = a.v[0];
+    } else {
+        bn_fr_t a = bn_fr_R2, b = bn_fr_R2; b.v[0] ^= 0x1234567;
+        for (long i = 0; i < iters; i++) bn_fr_mul(&a, &a, &b);
+        sink = a.v[0];
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    (void)sink;
+    return ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / (double)iters;
+}
+
+/* out[i] = scalars[i] * G for an affine generator G: the fixed-base multiplications of generator.rs:128-196
+ * (`FixedBase::msm`), used to build the synthetic proving key of the CPU reference arm without touching the GPU.
+ * 4-bit fixed windows over a table T[w][d] = d 16^w G, 64 mixed additions per point, one batched inversion
+ * (Montgomery's trick) per 256 points.  scalars canonical (n x 4 u64); out affine Montgomery, infinity as (0, 0). */
+#define FIXED_BASE_IMPL(NAME, G, FE, COORD_LIMBS)                                                                  \
+    static int NAME(const uint64_t* gen_xy, const uint64_t* scalars, size_t n, uint64_t* out_xy, int threads) {     \
+        init_all();                                                                                                \
+        if (threads < 1) threads = 1;                                                                              \
+        G##_aff g;                                                                                                 \
+        memcpy(&g.x, gen_xy, 8 * COORD_LIMBS); memcpy(&g.y, gen_xy + COORD_LIMBS, 8 * COORD_LIMBS); g.inf = 0;     \
+        G##_aff* tbl = (G##_aff*)malloc(sizeof(G##_aff) * 64 * 16);                                                \
+        G##_jac base; base.x = g.x; base.y = g.y; base.z = FE##_ONE;                                               \
+        for (int w = 0; w < 64; w++) {                                                                             \
+            G##_jac acc; G##_set_inf(&acc);                                                                        \
+            G##_aff b_aff; G##_to_affine(&b_aff, &base);                                                           \
+            memset(&tbl[w * 16], 0, sizeof(G##_aff)); tbl[w * 16].inf = 1;                                         \
+            for (int d = 1; d < 16; d++) { G##_add_mixed(&acc, &b_aff); G##_to_affine(&tbl[w * 16 + d], &acc); }   \
+            for (int k = 0; k < 4; k++) G##_dbl(&base);                                                            \
+        }                                                                                                          \
+        const size_t CH = 256;                                                                                     \
+        const size_t nch = (n + CH - 1) / CH;                                                                      \
+        _Pragma("omp parallel for num_threads(threads) schedule(dynamic, 4)")                                      \
+        for (size_t c = 0; c < nch; c++) {                                                                         \
+            G##_jac pt[256]; FE##_t pre[256];                                                                      \
+            size_t lo = c * CH, hi = lo + CH < n ? lo + CH : n;                                                    \
+            FE##_t run = FE##_ONE;                                                                                 \
+            for (size_t i = lo; i < hi; i++) {                                                                     \
+                G##_jac acc; G##_set_inf(&acc);                                                                    \
+                const uint64_t* k = scalars + 4 * i;                                                               \
+                for (int w = 0; w < 64; w++) {                                                                     \
+                    unsigned d = (unsigned)(k[w >> 4] >> ((w & 15) * 4)) & 15u;                                    \
+                    if (d) G##_add_mixed(&acc, &tbl[w * 16 + d]);                                                  \
+                }                                                                                                  \
+                pt[i - lo] = acc;                                                                                  \
+                pre[i - lo] = run;                                                                                 \
+                if (!G##_is_inf(&acc)) FE##_mul(&run, &run, &acc.z);                                               \
+            }                                                                                                      \
+            FE##_t inv; FE##_inv(&inv, &run);                                                                      \
+            for (size_t i = hi; i-- > lo;) {                                                                       \
+                uint64_t* o = out_xy + i * 2 * COORD_LIMBS;                                                        \
+                G##_jac* p = &pt[i - lo];                                                                          \
+                if (G##_is_inf(p)) { memset(o, 0, 16 * COORD_LIMBS); continue; }                                   \
+                FE##_t zi, zi2, t;                                                                                 \
+                FE##_mul(&zi, &inv, &pre[i - lo]);                                                                 \
+                FE##_mul(&inv, &inv, &p->z);                                                                       \
+                FE##_sqr(&zi2, &zi);                                                                               \
+                FE##_mul(&t, &p->x, &zi2); memcpy(o, &t, 8 * COORD_LIMBS);                                         \
+                FE##_mul(&zi2, &zi2, &zi);                                                                         \
+                FE##_mul(&t, &p->y, &zi2); memcpy(o + COORD_LIMBS, &t, 8 * COORD_LIMBS);                           \
+            }                                                                                                      \
+        }                                                                                                          \
+        free(tbl);                                                                                                 \
+        return 0;                                                                                                  \
+    }
+FIXED_BASE_IMPL(orc_fixed_bls_g1, bls_g1, bls_fq, 6)
+FIXED_BASE_IMPL(orc_fixed_bls_g2, bls_g2, bls_fq2, 12)
+FIXED_BASE_IMPL(orc_fixed_bn_g1, bn_g1, bn_fq, 4)
+FIXED_BASE_IMPL(orc_fixed_bn_g2, bn_g2, bn_fq2, 8)
+int orc_fixed_base_mul(int curve, int group, const uint64_t* gen_xy, const uint64_t* scalars, size_t n, uint64_t* out_xy,
+                       int threads) {
+    if (curve == 0) return group == 1 ? orc_fixed_bls_g1(gen_xy, scalars, n, out_xy, threads)
+                                      : orc_fixed_bls_g2(gen_xy, scalars, n, out_xy, threads);
+    return group == 1 ? orc_fixed_bn_g1(gen_xy, scalars, n, out_xy, threads)
+                      : orc_fixed_bn_g2(gen_xy, scalars, n, out_xy, threads);
 }
 
 /* ---- whole-proof restatement (prover.rs:53-156 + committer.rs:106-114) -------------------------

@@ -171,3 +171,27 @@ def dot_fr(curve_id, a, b, threads=0):
                           C.c_int(threads or (os.cpu_count() or 1)))
     assert rc == 0
     return sum(int(out[i]) << (64 * i) for i in range(4))
+
+
+def uses_asm():
+    """True when the MULX/ADCX/ADOX field multiplication is in use on this host."""
+    return bool(lib().orc_uses_asm())
+
+
+def bench_field_mul(curve_id, field, iters=2_000_000):
+    """ns per Montgomery multiplication (single thread, dependent chain); field 0 = Fr, 1 = Fq."""
+    fn = lib().orc_bench_field_mul
+    fn.restype = C.c_double
+    return float(fn(C.c_int(curve_id), C.c_int(field), C.c_long(iters)))
+
+
+def fixed_base_mul(curve_id, group, gen_xy, scalars, threads=0):
+    """out[i] = scalars[i] * G on the CPU: gen_xy affine Montgomery (2L | 4L limbs), scalars (n, 4) canonical ->
+    (n, 2L | 4L) affine Montgomery points, infinity as zeros.  (generator.rs:128-196 `FixedBase::msm`.)"""
+    gen_xy = np.ascontiguousarray(gen_xy, dtype=np.uint64).ravel()
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((scalars.shape[0], gen_xy.size), dtype=np.uint64)
+    rc = lib().orc_fixed_base_mul(C.c_int(curve_id), C.c_int(group), _p(gen_xy), _p(scalars), C.c_size_t(scalars.shape[0]),
+                                  _p(out), C.c_int(threads or (os.cpu_count() or 1)))
+    assert rc == 0
+    return out

@@ -240,15 +240,15 @@ def test_scalar_mul_matches_oracle(ctx, group):
 
 
 @pytest.mark.parametrize("opts", [
-    {B.OPT_GATHER_CAP: 2, B.OPT_FOLD_SEG: 4},                       # every run too long for the gather step -> fold levels
-    {B.OPT_GATHER_CAP: 3, B.OPT_FOLD_SEG: 16, B.OPT_ACCUM_SEG_MIN: 1},
-    {B.OPT_ACCUM_WAVES: 1, B.OPT_ACCUM_SEG_MIN: 2, B.OPT_GATHER_CAP: 4096},   # one wave, long gather walks
-    {B.OPT_ACCUM_SEG_MIN: 512, B.OPT_REDUCE_CHUNK: 16},             # a handful of threads own the whole list
+    {B.OPT_FOLD_SEG: 4, B.OPT_ACCUM_SEG_MIN: 1},                      # one item per thread: every run goes through the folds
+    {B.OPT_ACCUM_WAVES: 1, B.OPT_ACCUM_SEG_MIN: 2, B.OPT_FOLD_SEG: 32},   # grid capped at one wave: device-side segment length
+    {B.OPT_ACCUM_SEG_MIN: 512, B.OPT_REDUCE_CHUNK: 16},               # a handful of threads own the whole list
     {B.OPT_ACCUM_WAVES: 64, B.OPT_ACCUM_SEG_MIN: 3, B.OPT_FOLD_SEG: 8, B.OPT_REDUCE_CHUNK: 1},
+    {B.OPT_SORT_GLOBAL_ATOMICS: 1},                                   # table sets through the global-atomic sort
 ])
 def test_tuning_options_never_change_results(ctx, opts):
-    """hk_ctx_set_option: the accumulation geometry (waves, minimum segment), the gather cap and the fold /
-    reduction chunking only move work between kernels.  Forced to extreme values on a forked context and run over
+    """hk_ctx_set_option: the accumulation geometry (waves, minimum segment) and the fold / reduction chunking only
+    move work between kernels.  Forced to extreme values on a forked context and run over
     the cases that stress the segment borders: runs of every length 0..40 in one bucket, P + P, P - P, bases at
     infinity, uniform and witness-like scalars, G1 / G2, table and plain mode."""
     cv = ctx.curve

@@ -1,8 +1,7 @@
 #!/usr/bin/env python3
 """Checked timing of standalone window-table MSMs (uniform scalars), best of 5 after warm-up -- knob A/B helper.
 usage: msm_time.py GROUP LOG_N[,LOG_N...] [OPTSET ...]
-  OPTSET = comma-separated hk_ctx_set_option settings, e.g.  waves=2,smin=64  cap=2,fold=16  (names: waves smin fold
-  chunk cap); every OPTSET is timed on a fork of the same context (same bases, same scalars); "-" = defaults."""
+  OPTSET = comma-separated hk_ctx_set_option settings, e.g.  waves=2,smin=64  fold=16  (names: waves smin fold chunk); every OPTSET is timed on a fork of the same context (same bases, same scalars); "-" = defaults."""
 import os
 import sys
 
@@ -15,8 +14,7 @@ from hekaton_system_b200 import codec
 from hekaton_system_b200.backend import Context
 from sweep import best_ms, limb_dot_mod
 
-NAMES = {"waves": B.OPT_ACCUM_WAVES, "smin": B.OPT_ACCUM_SEG_MIN, "fold": B.OPT_FOLD_SEG, "chunk": B.OPT_REDUCE_CHUNK,
-         "cap": B.OPT_GATHER_CAP, "sortb": B.OPT_SORT_BLOCKS_PER_SM}
+NAMES = {"waves": B.OPT_ACCUM_WAVES, "smin": B.OPT_ACCUM_SEG_MIN, "fold": B.OPT_FOLD_SEG, "chunk": B.OPT_REDUCE_CHUNK, "gsort": B.OPT_SORT_GLOBAL_ATOMICS}
 
 group = int(sys.argv[1])
 sizes = [int(x) for x in sys.argv[2].split(",")]
