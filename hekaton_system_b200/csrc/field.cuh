@@ -399,4 +399,72 @@ struct Fp2T {
     __device__ __forceinline__ Fp2T to_mont() const { return {c0.to_mont(), c1.to_mont()}; }
 };
 
+// One Fq2 element spread over a LANE PAIR: the even lane of a pair (threadIdx.x & 1 == 0) holds c0, the odd lane c1.
+// Used by the G2 bucket accumulation (msm_impl.cuh: k_msm_accum_g2pair): an Fq2 point addition in one thread needs
+// 255 registers and still spills (2 CTAs per SM, 72 % of the multiplier peak, dependent-issue bound); split over two
+// lanes every lane carries half the state -- the register budget of the G1 kernel -- and issues ONE fused dual
+// product per Fq2 multiplication:
+//     even lane:  c0 = a0 b0 - a1 b1 = a0 b0 + (p - a1) b1          odd lane:  c1 = a1 b0 + a0 b1
+// after fetching the partner's halves with two pair-wide shuffles (24 SHFL of 32 bits for BLS12-381, against 444
+// wide multiplies).  Squaring: even lane (a0 + a1)(a0 - a1), odd lane (2 a1) a0 -- one multiplication each.
+// Additions / subtractions are component-wise.  Predicates (is_zero, ==) combine both halves, so every branch the
+// point arithmetic takes is uniform within a pair and the shuffles (masked to the pair) are always converged.
+// Only for base fields with the fused dual product (BLS12-381 Fq); blockDim.x must be even.
+template <class F>
+struct Fp2Half {
+    using base = F;
+    F v;
+    __device__ __forceinline__ static unsigned pair_mask() { return 3u << ((threadIdx.x & 31u) & ~1u); }
+    __device__ __forceinline__ static bool odd() { return (threadIdx.x & 1u) != 0; }
+    __device__ __forceinline__ static F partner(const F& x) {
+        F o;
+        const unsigned m = pair_mask();
+#pragma unroll
+        for (int i = 0; i < F::N64; i++) o.r.v[i] = __shfl_xor_sync(m, x.r.v[i], 1);
+        return o;
+    }
+    __device__ __forceinline__ static F sel(bool take_a, const F& a, const F& b) {
+        F o;
+#pragma unroll
+        for (int i = 0; i < F::N64; i++) o.r.v[i] = take_a ? a.r.v[i] : b.r.v[i];
+        return o;
+    }
+    __device__ __forceinline__ static Fp2Half zero() { return {F::zero()}; }
+    __device__ __forceinline__ static Fp2Half one() { return {sel(odd(), F::zero(), F::one())}; }
+    __device__ __forceinline__ bool is_zero() const {
+        const bool z = v.is_zero();
+        return z && __shfl_xor_sync(pair_mask(), z, 1);
+    }
+    __device__ __forceinline__ bool operator==(const Fp2Half& b) const {
+        const bool e = v == b.v;
+        return e && __shfl_xor_sync(pair_mask(), e, 1);
+    }
+    __device__ __forceinline__ bool operator!=(const Fp2Half& b) const { return !(*this == b); }
+    __device__ __forceinline__ Fp2Half operator+(const Fp2Half& b) const { return {v + b.v}; }
+    __device__ __forceinline__ Fp2Half operator-(const Fp2Half& b) const { return {v - b.v}; }
+    __device__ __forceinline__ Fp2Half dbl() const { return {v.dbl()}; }
+    __device__ __forceinline__ Fp2Half neg() const { return {v.neg()}; }
+    __device__ __forceinline__ Fp2Half operator*(const Fp2Half& b) const {
+        static_assert(F::HAS_MUL2, "Fp2Half needs the fused dual product");
+        const bool o = odd();
+        const F pa = partner(v), pb = partner(b.v);
+        // even: v * b.v + (p - pa) * pb        odd: v * pb + pa * b.v
+        const F x2 = sel(o, pa, pa.neg_raw());
+        const F y1 = sel(o, pb, b.v);
+        const F y2 = sel(o, b.v, pb);
+        return {F::mul_add_mul(v, y1, x2, y2)};
+    }
+    __device__ __forceinline__ Fp2Half sqr() const {
+        const bool o = odd();
+        const F pa = partner(v);
+        const F x = sel(o, v.dbl(), v + pa);     // odd: 2 a1        even: a0 + a1
+        const F y = sel(o, pa, v - pa);          // odd: a0          even: a0 - a1
+        return {x * y};
+    }
+    __device__ __forceinline__ static Fp2Half mul_sub_mul(const Fp2Half& a, const Fp2Half& b, const Fp2Half& c,
+                                                          const Fp2Half& d) {
+        return a * b - c * d;
+    }
+};
+
 }  // namespace hk

@@ -380,6 +380,72 @@ k_msm_accum(const Affine<F>* __restrict__ bases, const uint64_t* __restrict__ pa
     partial_keys[2 * (size_t)t + 1] = k1;
 }
 
+// G2 over a field with the fused dual product: the same segment scheme with every Fq2 value spread over a lane pair
+// (field.cuh Fp2Half).  Pair t owns segment t; both lanes walk the same sorted pairs (one broadcast load), each loads
+// and stores its half of every coordinate (Fq2 = c0 || c1 in memory, so the halves of a coordinate are adjacent).
+// Buckets and partial sums keep the XYZZ<Fq2> memory layout: the fold / reduce kernels are unchanged.
+template <class F2, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_msm_accum_g2pair(const Affine<F2>* __restrict__ bases, const uint64_t* __restrict__ pairs,
+                   const uint32_t* __restrict__ d_count, uint32_t s_min, XYZZ<F2>* buckets, XYZZ<F2>* partial,
+                   uint32_t* partial_keys, uint32_t npairs) {
+    using Fb = typename F2::base;
+    using H = Fp2Half<Fb>;
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = g >> 1, par = g & 1u;
+    if (t >= npairs) return;
+    const uint32_t count = *d_count;
+    uint32_t S = (count + npairs - 1) / npairs;
+    if (S < s_min) S = s_min;
+    const size_t lo = (size_t)t * S;
+    uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
+    auto store = [par](XYZZ<F2>* dst, const XYZZ<H>& a) {
+        Fb* d = reinterpret_cast<Fb*>(dst);
+        d[0 + par] = a.x.v;
+        d[2 + par] = a.y.v;
+        d[4 + par] = a.zz.v;
+        d[6 + par] = a.zzz.v;
+    };
+    if (lo < count) {
+        const size_t hi = lo + S < count ? lo + S : count;
+        uint32_t cur = (uint32_t)(pairs[lo] >> 32);
+        const uint32_t first_key = cur;
+        XYZZ<H> acc = XYZZ<H>::inf();
+        bool first_done = false;
+        for (size_t i = lo; i < hi; i++) {
+            const uint64_t pr = pairs[i];
+            const uint32_t k = (uint32_t)(pr >> 32);
+            if (k != cur) {
+                if (!first_done) {
+                    store(&partial[2 * (size_t)t], acc);
+                    first_done = true;
+                } else {
+                    store(&buckets[cur], acc);
+                }
+                acc = XYZZ<H>::inf();
+                cur = k;
+            }
+            const uint32_t it = (uint32_t)pr;
+            const Fb* src = reinterpret_cast<const Fb*>(bases + (it >> 1));
+            Affine<H> p;
+            p.x.v = src[0 + par];
+            p.y.v = src[2 + par];
+            acc.madd(p, it & 1);
+        }
+        k0 = first_key;
+        if (!first_done) {
+            store(&partial[2 * (size_t)t], acc);     // whole segment is one run
+        } else {
+            store(&partial[2 * (size_t)t + 1], acc);
+            k1 = cur;
+        }
+    }
+    if (par == 0) {
+        partial_keys[2 * (size_t)t] = k0;
+        partial_keys[2 * (size_t)t + 1] = k1;
+    }
+}
+
 // Level >= 1: same scheme over a list of XYZZ partials (full adds); empty slots skipped.
 // `final_level`: single thread range covers everything -> all runs are complete.
 // (A run that is cut by a high-order thread border stays split until the level whose segments swallow that border,
@@ -719,8 +785,21 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     }
     if (sb != ctx->lane_stream(so.lane)) HK_CUDA(cudaStreamWaitEvent(sb, ctx->ev_sorted[so.lane], 0));
     int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2, sb);
-    k_msm_accum<F, MINB><<<ceil_div(nthr0, 128), 128, 0, sb>>>(d_bases, so.pairs, so.d_count, s_min, buckets, partial,
-                                                               partial_keys, nthr0);
+    bool launched = false;
+#if defined(HK_MUL2) && !defined(HK_NO_G2_PAIR)
+    if constexpr (GROUP == 2) {
+        if constexpr (F::base::HAS_MUL2) {      // an Fq2 point addition split over a lane pair (field.cuh Fp2Half)
+            if (!ctx->opt_g2_single) {
+                k_msm_accum_g2pair<F, 3><<<ceil_div(2 * (size_t)nthr0, 128), 128, 0, sb>>>(d_bases, so.pairs, so.d_count, s_min,
+                                                                                        buckets, partial, partial_keys, nthr0);
+                launched = true;
+            }
+        }
+    }
+#endif
+    if (!launched)
+        k_msm_accum<F, MINB><<<ceil_div(nthr0, 128), 128, 0, sb>>>(d_bases, so.pairs, so.d_count, s_min, buckets, partial,
+                                                                   partial_keys, nthr0);
     HK_LAUNCH_CHECK(ctx);
     prof_end(ctx, pi, 0, so.d_count, sb);
     if (sb != st) {
