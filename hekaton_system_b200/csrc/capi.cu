@@ -391,7 +391,7 @@ HK_EXPORT int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out) {
     ctx->opt_fold_seg = parent->opt_fold_seg;
     ctx->opt_reduce_g = parent->opt_reduce_g;
     ctx->opt_sort_global = parent->opt_sort_global;
-    ctx->opt_g2_single = parent->opt_g2_single;
+    ctx->opt_g2_pair = parent->opt_g2_pair;
     if (cudaSetDevice(ctx->device) != cudaSuccess) {
         delete ctx;
         return HK_ERR_CUDA;
@@ -436,7 +436,7 @@ HK_EXPORT int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value
                 ctx->opt_reduce_g = (uint32_t)value;
                 break;
             case HK_OPT_SORT_GLOBAL_ATOMICS: ctx->opt_sort_global = value ? 1u : 0u; break;
-            case HK_OPT_G2_SINGLE_LANE: ctx->opt_g2_single = value ? 1u : 0u; break;
+            case HK_OPT_G2_LANE_PAIR: ctx->opt_g2_pair = value ? 1u : 0u; break;
             default: throw HkError{HK_ERR_INVALID, "unknown option"};
         }
     });

@@ -433,11 +433,13 @@ struct Fp2Half {
     __device__ __forceinline__ static Fp2Half one() { return {sel(odd(), F::zero(), F::one())}; }
     __device__ __forceinline__ bool is_zero() const {
         const bool z = v.is_zero();
-        return z && __shfl_xor_sync(pair_mask(), z, 1);
+        const bool pz = __shfl_xor_sync(pair_mask(), z, 1) != 0;       // both lanes must reach the shuffle: no short circuit
+        return z && pz;
     }
     __device__ __forceinline__ bool operator==(const Fp2Half& b) const {
         const bool e = v == b.v;
-        return e && __shfl_xor_sync(pair_mask(), e, 1);
+        const bool pe = __shfl_xor_sync(pair_mask(), e, 1) != 0;
+        return e && pe;
     }
     __device__ __forceinline__ bool operator!=(const Fp2Half& b) const { return !(*this == b); }
     __device__ __forceinline__ Fp2Half operator+(const Fp2Half& b) const { return {v + b.v}; }

@@ -787,10 +787,14 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2, sb);
     bool launched = false;
 #if defined(HK_MUL2) && !defined(HK_NO_G2_PAIR)
+    // Opt-in (HK_OPT_G2_LANE_PAIR): an Fq2 point addition split over a lane pair (field.cuh Fp2Half).  Measured on B200
+    // (profiles/r02_summary.md): bit-identical, +1.4 % proofs/s and -1 ... -6 % on a standalone G2 MSM at best -- the
+    // multiplication body, not the per-lane point state, dominates the register budget (230 registers without spills),
+    // so the occupancy stays at 2 CTAs per SM and the kernel remains dependent-issue bound.  Off by default.
     if constexpr (GROUP == 2) {
-        if constexpr (F::base::HAS_MUL2) {      // an Fq2 point addition split over a lane pair (field.cuh Fp2Half)
-            if (!ctx->opt_g2_single) {
-                k_msm_accum_g2pair<F, 3><<<ceil_div(2 * (size_t)nthr0, 128), 128, 0, sb>>>(d_bases, so.pairs, so.d_count, s_min,
+        if constexpr (F::base::HAS_MUL2) {
+            if (ctx->opt_g2_pair) {
+                k_msm_accum_g2pair<F, 2><<<ceil_div(2 * (size_t)nthr0, 128), 128, 0, sb>>>(d_bases, so.pairs, so.d_count, s_min,
                                                                                         buckets, partial, partial_keys, nthr0);
                 launched = true;
             }
