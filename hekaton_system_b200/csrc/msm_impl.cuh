@@ -450,8 +450,8 @@ k_msm_accum_g2pair(const Affine<F2>* __restrict__ bases, const uint64_t* __restr
 // `final_level`: single thread range covers everything -> all runs are complete.
 // (A run that is cut by a high-order thread border stays split until the level whose segments swallow that border,
 // so the chain runs all its levels: log2 of the list length, each a handful of dependent additions.)
-template <class F, int S>
-__global__ void __launch_bounds__(128)
+template <class F, int S, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_msm_fold(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys, uint32_t n_in,
            XYZZ<F>* buckets, XYZZ<F>* out, uint32_t* out_keys, uint32_t nthreads, int final_level) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -748,6 +748,9 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     // fold segment length (levels that remain after the gather step): 16 inside a proof batch (few launches; the
     // tails hide under other lanes' accumulations), 4 for a standalone MSM (short serial chains)
     const int S1 = ctx->opt_fold_seg ? (int)ctx->opt_fold_seg : (lane == 0 ? 4 : 16);
+    // (Measured and rejected, profiles/r02_summary.md: 4-entry segments for the first three levels and 16-entry ones
+    // for the mostly empty late levels -- 9 instead of 19 launches at 2^20 -- is SLOWER, 7.55 vs 7.31 ms: a late level
+    // costs the latency of its longest thread, and 16-entry threads are longer.)
     std::vector<uint32_t> lvl_in;      // entries consumed at fold level l
     {
         uint32_t cur = 2 * nthr0;
@@ -819,10 +822,12 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
         uint32_t* in_keys = partial_keys + off;
         XYZZ<F>* out = partial + off + n_in;
         uint32_t* out_keys = partial_keys + off + n_in;
-        if (S1 == 8) k_msm_fold<F, 8><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
-        else if (S1 == 4) k_msm_fold<F, 4><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
-        else if (S1 == 32) k_msm_fold<F, 32><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
-        else k_msm_fold<F, 16><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level);
+#define HK_FOLD(SS) k_msm_fold<F, SS, 1><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level)
+        if (S1 == 8) HK_FOLD(8);
+        else if (S1 == 4) HK_FOLD(4);
+        else if (S1 == 32) HK_FOLD(32);
+        else HK_FOLD(16);
+#undef HK_FOLD
         HK_LAUNCH_CHECK(ctx);
         off += n_in;
     }
