@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 #include "../../include/hekaton_b200.h"
 #include "ec.cuh"
 
@@ -257,6 +259,17 @@ struct hk_ctx {
 namespace hk {
 
 inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// NVTX range over the ENQUEUE of a pipeline stage, named after the reference's timers (ark_std start_timer! labels in
+// cp-groth16/src/prover.rs:58-150 and committer.rs:59-96), so an nsys / ncu timeline of this library lines up with
+// the reference's --features print-trace output.  The kernels run asynchronously on the lane streams; tools
+// attribute them to the range that launched them.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // Wraps every extern "C" body: activates the device, maps exceptions to codes.
 template <class Fn>

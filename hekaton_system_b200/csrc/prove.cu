@@ -450,6 +450,7 @@ void commit_run(hk_ctx* ctx, PkDev& pk, uint32_t stage, size_t K, const uint64_t
     using Fq = typename Curve::Fq;
     HK_REQUIRE(stage < pk.num_stages, HK_ERR_INVALID, "commit: no such stage (\"no more values left in committing key\")");
     if (K == 0) return;
+    NvtxRange nvtx_commit("Groth16::Commit");                  // committer.rs:59
     const size_t l = pk.r1cs->l;
     const size_t nw = pk.stage_start[stage + 1] - pk.stage_start[stage];
     // a commitment is a small latency-bound MSM: run it on a prioritised lane so that, when other
@@ -478,6 +479,7 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     using Fq = typename Curve::Fq;
     using Fq2 = typename Curve::Fq2;
     if (K == 0) return;
+    NvtxRange nvtx_prover("Groth16::Prover");                  // prover.rs:58
     const Fr* z = reinterpret_cast<const Fr*>(d_z_v);
     const Fr* r = reinterpret_cast<const Fr*>(d_r);
     const Fr* s = reinterpret_cast<const Fr*>(d_s);
@@ -503,15 +505,20 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     enum { LA = 1, LB1 = 2, LB2 = 3, LH = 4, LL = 5 };
     HK_CUDA(cudaEventRecord(ctx->ev_fork, st));
     for (int ln = 1; ln < hk_ctx::LANES; ln++) HK_CUDA(cudaStreamWaitEvent(ctx->lane_stream(ln), ctx->ev_fork, 0));
-    msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, Sr, K, false, jac + 0, 0, LA);
+    {
+        NvtxRange r_("Compute A");                             // prover.rs:84
+        msm_run<Curve, 1>(ctx, msm_view(pk.a_ext), 0, m + 2, Sr, K, false, jac + 0, 0, LA);
+    }
     HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LA], ctx->lane_stream(LA)));
     MsmSorted sorted_s;
+    nvtxRangePushA("Compute B in G1");                         // prover.rs:94
     if (pk.share_b_sort) {
         sorted_s = msm_sort<Curve>(ctx, msm_view(pk.b1_ext), 0, m + 2, Ss, K, false, 0, LB1);
         msm_accumulate<Curve, 1>(ctx, sorted_s, msm_view(pk.b1_ext), jac + K, LB1);
     } else {
         msm_run<Curve, 1>(ctx, msm_view(pk.b1_ext), 0, m + 2, Ss, K, false, jac + K, 0, LB1);
     }
+    nvtxRangePop();
     // s*A, r*B1 and A's normalisation, on B1's control stream once A is there too
     XYZZ<Fq>* sab = ctx->ws_io[2].as<XYZZ<Fq>>(2 * K);
     HK_CUDA(cudaStreamWaitEvent(ctx->lane_stream(LB1), ctx->ev_lane_done[LA], 0));
@@ -520,6 +527,7 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     HK_LAUNCH_CHECK(ctx);
     HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LB1], ctx->lane_stream(LB1)));
     // the G2 MSM + B2's normalisation
+    nvtxRangePushA("Compute B in G2");                         // prover.rs:105
     if (pk.share_b_sort)
         msm_accumulate<Curve, 2>(ctx, sorted_s, msm_view(pk.b2_ext), jacB2, LB2);     // same scalars, same list
     else
@@ -527,23 +535,31 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
     k_prove_finish_b2<Curve><<<Ku, 32, 0, ctx->lane_stream(LB2)>>>(jacB2, reinterpret_cast<Affine<Fq2>*>(d_outB), d_inf);
     HK_LAUNCH_CHECK(ctx);
     HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LB2], ctx->lane_stream(LB2)));
+    nvtxRangePop();
     // witness map, then the H MSM (they need only z)
     uint64_t* abc = ctx->ws_qap[0].as<uint64_t>(4 * 3 * N * K);
     uint64_t* h = ctx->ws_qap[1].as<uint64_t>(4 * N * K);
     ntt_domain<Curve>(ctx, log_n);                 // build (and synchronise) the tables before switching streams
     ctx->qap_stream = ctx->lane_stream(LH);
+    nvtxRangePushA("R1CS to QAP witness map");                 // prover.rs:122
     try {
         r1cs_evals<Curve>(ctx, *pk.r1cs, d_z_v, abc, K);
         qap_h_from_evals<Curve>(ctx, log_n, abc, h, K);
     } catch (...) {
         ctx->qap_stream = nullptr;
+        nvtxRangePop();
         throw;
     }
     ctx->qap_stream = nullptr;
-    msm_run<Curve, 1>(ctx, msm_view(*pk.h_g), 0, N - 1, reinterpret_cast<const Scalar256*>(h), K, true, jac + 3 * K,
-                      /*sc_stride=*/N, LH);
+    nvtxRangePop();
+    {
+        NvtxRange r_("Compute H");                             // prover.rs:127
+        msm_run<Curve, 1>(ctx, msm_view(*pk.h_g), 0, N - 1, reinterpret_cast<const Scalar256*>(h), K, true, jac + 3 * K,
+                          /*sc_stride=*/N, LH);
+    }
     HK_CUDA(cudaEventRecord(ctx->ev_lane_done[LH], ctx->lane_stream(LH)));
     // L'
+    NvtxRange nvtx_l("Compute L");                             // prover.rs:112
     const size_t nl = pk.stage_start[ns] - pk.stage_start[ns - 1];
     Fr* Ls = ctx->ws_io[1].as<Fr>(K * (nl + ns));
     k_build_l_scalars<Fr><<<dim3(ceil_div(nl + ns, 256), Ku), 256, 0, ctx->lane_stream(LL)>>>(
@@ -553,6 +569,7 @@ void prove_run(hk_ctx* ctx, PkDev& pk, size_t K, const uint64_t* d_z_v, const ui
                       jac + 2 * K, 0, LL);
     // C = s*A + r*B1 + L' + H on L''s control stream (the caller's stream usually has the lowest priority
     // and would be served only after every queued accumulation of the batches behind this one)
+    NvtxRange nvtx_c("Finish C");                              // prover.rs:140
     cudaStream_t fin = ctx->lane_stream(LL);
     for (int ln : {LB1, LH}) HK_CUDA(cudaStreamWaitEvent(fin, ctx->ev_lane_done[ln], 0));
     k_prove_finish_c<Curve><<<Ku, 32, 0, fin>>>(sab, jac + 2 * K, jac + 3 * K, reinterpret_cast<Affine<Fq>*>(d_outC), d_inf,
