@@ -46,6 +46,25 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f
+    # the build path as well: the field-kernel generator and the Rust binding generator take their constants from the
+    # product's own tables, and the host mirror / ABI header never mention the oracle
+    for rel in ("tools/gen_field.py", "tools/gen_rust_sys.py", "host/cp_groth16.hpp", "host/hk_node.cpp",
+                "include/hekaton_b200.h"):
+        txt = open(os.path.join(ROOT, rel)).read()
+        assert "import oracle" not in txt and "from oracle" not in txt, rel
+
+
+def test_generated_field_header_is_current_and_oracle_free():
+    """Regenerating csrc/field_gen.cuh with the oracle package made unimportable gives the committed file: the
+    kernels' constants come from hekaton_system_b200/curves.py alone."""
+    import subprocess
+    import sys
+    import tempfile
+    out = os.path.join(tempfile.mkdtemp(), "field_gen.cuh")
+    code = ("import sys, runpy; sys.modules['oracle'] = None; sys.argv = ['gen_field.py', '--out', %r]; "
+            "runpy.run_path(%r, run_name='__main__')" % (out, os.path.join(ROOT, "tools", "gen_field.py")))
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.DEVNULL)
+    assert open(out).read() == open(os.path.join(ROOT, "hekaton_system_b200", "csrc", "field_gen.cuh")).read()
 
 
 def test_default_build_uses_the_fused_dual_product():

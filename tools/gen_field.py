@@ -816,7 +816,9 @@ class FieldGen:
 
 
 def field_list():
-    from oracle.params import BLS12_381, BN254
+    # the product's own copy of the curve constants (never the oracle's: a wrong constant there would otherwise be
+    # baked into the kernels AND the checker)
+    from hekaton_system_b200.curves import BLS12_381, BN254
     return [
         ("bls12_381_fq", BLS12_381.p),
         ("bls12_381_fr", BLS12_381.r),
@@ -828,12 +830,13 @@ def field_list():
 def extra_constants():
     """Fr-only constants (Montgomery form): 2-adic root of unity and F::GENERATOR
     (ark-ff FftField::TWO_ADIC_ROOT_OF_UNITY / GENERATOR)."""
-    from oracle.params import BLS12_381, BN254
+    from hekaton_system_b200.curves import BLS12_381, BN254
     out = {}
     for c in (BLS12_381, BN254):
         R = 1 << 256
+        two_adic_root = pow(c.fr_generator, (c.r - 1) >> c.two_adicity, c.r)
         out[c.name + "_fr"] = [
-            ("ROOT", c.two_adic_root * R % c.r, "TWO_ADIC_ROOT_OF_UNITY * R mod r"),
+            ("ROOT", two_adic_root * R % c.r, "TWO_ADIC_ROOT_OF_UNITY * R mod r"),
             ("GEN", c.fr_generator * R % c.r, "F::GENERATOR * R mod r"),
         ]
     return out
