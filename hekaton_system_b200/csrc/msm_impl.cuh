@@ -547,6 +547,104 @@ k_msm_tree_sum(const XYZZ<F>* __restrict__ in, uint32_t m, uint32_t in_stride, X
     if (threadIdx.x == 0) out[(size_t)blockIdx.y * out_stride + blockIdx.x] = sh[0];
 }
 
+// ---- quad-cooperative variants of the latency-bound kernels (ec.cuh: quad_add / quad_dbl) -----------------
+// Same lists, same outputs, four lanes per logical thread.  Used whenever the single-lane grid could not fill the GPU
+// (late fold levels, the bucket reduction, the tree sums): there the kernel's duration is the longest dependent chain
+// of point additions, and a quad walks it 3.3x faster.
+template <class F, int S>
+__global__ void __launch_bounds__(128)
+k_msm_fold_quad(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys, uint32_t n_in,
+                XYZZ<F>* buckets, XYZZ<F>* out, uint32_t* out_keys, uint32_t nthreads, int final_level) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = g >> 2;
+    const bool lead = (g & 3u) == 0;
+    if (t >= nthreads) return;
+    size_t lo = (size_t)t * S;
+    size_t hi = lo + S < n_in ? lo + S : n_in;
+    uint32_t cur = KEY_NONE, first_key = KEY_NONE;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    bool first_done = false;
+    for (size_t i = lo; i < hi; i++) {
+        uint32_t k = in_keys[i];
+        if (k == KEY_NONE) continue;
+        if (cur == KEY_NONE) {
+            cur = k;
+            first_key = k;
+        } else if (k != cur) {
+            if (!first_done && !final_level) {
+                if (lead) out[2 * (size_t)t] = acc;
+            } else {
+                if (lead) buckets[cur] = acc;
+            }
+            first_done = true;
+            acc = XYZZ<F>::inf();
+            cur = k;
+        }
+        acc = quad_add(acc, in[i]);
+    }
+    uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
+    if (cur != KEY_NONE) {
+        if (final_level) {
+            if (lead) buckets[cur] = acc;
+        } else if (!first_done) {
+            if (lead) out[2 * (size_t)t] = acc;
+            k0 = first_key;
+        } else {
+            if (lead) out[2 * (size_t)t + 1] = acc;
+            k0 = first_key;
+            k1 = cur;
+        }
+    }
+    if (!final_level && lead) {
+        out_keys[2 * (size_t)t] = k0;
+        out_keys[2 * (size_t)t + 1] = k1;
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+k_msm_reduce_chunks_quad(const XYZZ<F>* __restrict__ buckets, uint32_t B, uint32_t G, uint32_t T, uint32_t W,
+                         XYZZ<F>* chunk_out) {
+    const uint32_t gq = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t g = gq >> 2;
+    if (g >= T * W) return;
+    uint32_t w = g / T, t = g % T;
+    const XYZZ<F>* bk = buckets + (size_t)w * B + (size_t)t * G;
+    XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+    for (int j = (int)G - 1; j >= 0; j--) {
+        run = quad_add(run, bk[j]);
+        acc = quad_add(acc, run);
+    }
+    if (t != 0) acc = quad_add(acc, quad_mul_small(run, t * G));
+    if ((gq & 3u) == 0) chunk_out[g] = acc;
+}
+
+// every block adds 2 * TPB consecutive inputs of set blockIdx.y with TPB quads (blockDim.x = 4 * TPB)
+template <class F, int TPB>
+__global__ void __launch_bounds__(4 * TPB)
+k_msm_tree_sum_quad(const XYZZ<F>* __restrict__ in, uint32_t m, uint32_t in_stride, XYZZ<F>* out, uint32_t out_stride) {
+    extern __shared__ unsigned char smem_raw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    const XYZZ<F>* src = in + (size_t)blockIdx.y * in_stride;
+    const uint32_t qi = threadIdx.x >> 2;
+    const bool lead = (threadIdx.x & 3u) == 0;
+    const uint32_t i0 = blockIdx.x * 2 * TPB + qi;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (i0 < m) acc = src[i0];
+    if (i0 + TPB < m) acc = quad_add(acc, src[i0 + TPB]);
+    if (lead) sh[qi] = acc;
+    __syncthreads();
+    for (int off = TPB / 2; off > 0; off >>= 1) {
+        XYZZ<F> a = XYZZ<F>::inf();
+        const bool work = (int)qi < off;
+        if (work) a = quad_add(sh[qi], sh[qi + off]);
+        __syncthreads();                       // every quad has read its two inputs
+        if (work && lead) sh[qi] = a;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[(size_t)blockIdx.y * out_stride + blockIdx.x] = sh[0];
+}
+
 // tbl[w*n + i] = 2^(c w) * P_i, affine (one inversion per entry; one-off per base set)
 template <class F>
 __global__ void __launch_bounds__(128)
@@ -566,14 +664,14 @@ k_msm_precompute(const Affine<F>* __restrict__ pts, size_t n, int c, int W, Affi
 // one block per scalar vector: Horner over its W window sums (W = 1 in table mode: no doublings)
 template <class F>
 __global__ void k_msm_combine(const XYZZ<F>* __restrict__ wsum_all, int W, int c, Jacobian<F>* out) {
-    if (threadIdx.x != 0) return;
+    if (threadIdx.x >= 4) return;              // one quad per scalar vector (ec.cuh quad_dbl / quad_add)
     const XYZZ<F>* wsum = wsum_all + (size_t)blockIdx.x * W;
     XYZZ<F> acc = wsum[W - 1];
     for (int w = W - 2; w >= 0; w--) {
-        for (int k = 0; k < c; k++) acc = acc.dbl();
-        acc.add(wsum[w]);
+        for (int k = 0; k < c; k++) acc = quad_dbl(acc);
+        acc = quad_add(acc, wsum[w]);
     }
-    out[blockIdx.x] = Jacobian<F>::from_xyzz(acc);
+    if (threadIdx.x == 0) out[blockIdx.x] = Jacobian<F>::from_xyzz(acc);
 }
 
 template <class F>
@@ -668,8 +766,9 @@ MsmSorted msm_sort(hk_ctx* ctx, const MsmBases& bv, size_t offset, size_t n, con
     const size_t smem_bytes = (size_t)pl.B * sizeof(uint32_t);
     uint32_t J = 0;
     if (so.table && smem_bytes <= 160 * 1024 && !ctx->opt_sort_global) {
-        const uint32_t per_sm = smem_bytes > 100 * 1024 ? 1u : 2u;
-        uint64_t want = ((uint64_t)ctx->sm_count * per_sm * 2 + K - 1) / K;
+        // one wave of blocks when a block takes a whole SM (every extra block adds B counters to the scan), else two
+        const uint32_t per_sm = smem_bytes > 100 * 1024 ? 1u : 4u;
+        uint64_t want = ((uint64_t)ctx->sm_count * per_sm + K - 1) / K;
         const uint64_t most = (n + 1023) / 1024;
         if (want > most) want = most;
         if (want < 1) want = 1;
@@ -748,6 +847,12 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     // fold segment length (levels that remain after the gather step): 16 inside a proof batch (few launches; the
     // tails hide under other lanes' accumulations), 4 for a standalone MSM (short serial chains)
     const int S1 = ctx->opt_fold_seg ? (int)ctx->opt_fold_seg : (lane == 0 ? 4 : 16);
+    // Launches of at most this many logical threads cannot fill the GPU (148 SMs x 256 resident fold threads): they
+    // are latency-bound and, in a STANDALONE MSM (lane 0), run quad-cooperatively -- 2^16: 1.43 -> 1.07 ms (G1),
+    // 4.06 -> 2.85 ms (G2).  Inside a proof batch the tails hide under other lanes' accumulations and the quad
+    // kernels' ~20 % extra multiplier work costs throughput (286 vs 287 proofs/s), so the lanes keep one thread per
+    // addition.  (HK_OPT_QUAD_MAX_THREADS overrides the limit for every lane; 1 = never.)
+    const size_t quad_max = ctx->opt_quad_max ? ctx->opt_quad_max : (lane == 0 ? 32768 : 1);
     // (Measured and rejected, profiles/r02_summary.md: 4-entry segments for the first three levels and 16-entry ones
     // for the mostly empty late levels -- 9 instead of 19 launches at 2^20 -- is SLOWER, 7.55 vs 7.31 ms: a late level
     // costs the latency of its longest thread, and 16-entry threads are longer.)
@@ -769,7 +874,10 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     // reduction geometry: short serial chunks, then a multi-block tree
     // standalone (lane 0): short chunks shorten the serial tail; inside a proof batch the larger grids of a
     // latency-bound kernel take SM slots from the accumulations, so the lanes keep long chunks
-    uint32_t G = lane == 0 ? (pl.B >= 64 ? 2 : 1) : (pl.B >= 32768 ? 8 : (pl.B >= 1024 ? 4 : (pl.B >= 64 ? 2 : 1)));
+    // (lane 0 with the quad-cooperative kernels: 4 buckets per quad from B = 8192 on -- 2^20: 7.10 -> 6.95 ms, 2^18:
+    // 2.54 -> 2.37 ms; below that 2 -- the scalar multiplication of the chunk offset dominates a chunk's chain)
+    uint32_t G = lane == 0 ? (pl.B >= 8192 ? 4 : (pl.B >= 64 ? 2 : 1))
+                           : (pl.B >= 32768 ? 8 : (pl.B >= 1024 ? 4 : (pl.B >= 64 ? 2 : 1)));
     if (ctx->opt_reduce_g > 0 && ctx->opt_reduce_g <= pl.B) G = ctx->opt_reduce_g;
     uint32_t T = pl.B / G;
     constexpr int TS_TPB = 64;
@@ -822,7 +930,13 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
         uint32_t* in_keys = partial_keys + off;
         XYZZ<F>* out = partial + off + n_in;
         uint32_t* out_keys = partial_keys + off + n_in;
-#define HK_FOLD(SS) k_msm_fold<F, SS, 1><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level)
+#define HK_FOLD(SS)                                                                                                      \
+    do {                                                                                                                \
+        if (thr <= quad_max)                                                                                            \
+            k_msm_fold_quad<F, SS><<<ceil_div(4 * (size_t)thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level); \
+        else                                                                                                            \
+            k_msm_fold<F, SS, 1><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level); \
+    } while (0)
         if (S1 == 8) HK_FOLD(8);
         else if (S1 == 4) HK_FOLD(4);
         else if (S1 == 32) HK_FOLD(32);
@@ -831,14 +945,20 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
         HK_LAUNCH_CHECK(ctx);
         off += n_in;
     }
-    k_msm_reduce_chunks<F><<<ceil_div((size_t)T * nsets, 128), 128, 0, st>>>(buckets, pl.B, G, T, nsets, chunk_out);
+    if ((size_t)T * nsets <= quad_max)
+        k_msm_reduce_chunks_quad<F><<<ceil_div(4 * (size_t)T * nsets, 128), 128, 0, st>>>(buckets, pl.B, G, T, nsets, chunk_out);
+    else
+        k_msm_reduce_chunks<F><<<ceil_div((size_t)T * nsets, 128), 128, 0, st>>>(buckets, pl.B, G, T, nsets, chunk_out);
     HK_LAUNCH_CHECK(ctx);
     XYZZ<F>* cur = chunk_out;
     uint32_t cur_stride = T;
     XYZZ<F>* nxt = chunk_out + (size_t)T * nsets;
     for (uint32_t m : tree) {
         uint32_t nb = ceil_div(m, 2 * TS_TPB);
-        k_msm_tree_sum<F, TS_TPB><<<dim3(nb, nsets), TS_TPB, TS_TPB * sizeof(XYZZ<F>), st>>>(cur, m, cur_stride, nxt, nb);
+        if ((size_t)nb * nsets * TS_TPB <= quad_max)
+            k_msm_tree_sum_quad<F, TS_TPB><<<dim3(nb, nsets), 4 * TS_TPB, TS_TPB * sizeof(XYZZ<F>), st>>>(cur, m, cur_stride, nxt, nb);
+        else
+            k_msm_tree_sum<F, TS_TPB><<<dim3(nb, nsets), TS_TPB, TS_TPB * sizeof(XYZZ<F>), st>>>(cur, m, cur_stride, nxt, nb);
         HK_LAUNCH_CHECK(ctx);
         cur = nxt;
         cur_stride = nb;

@@ -73,6 +73,22 @@ __device__ __noinline__ XYZZ<F> scalar_mul(const XYZZ<F>& p, const uint64_t k[4]
     return acc;
 }
 
+// the same, four lanes per multiplication (ec.cuh quad_add / quad_dbl): 3.3x shorter dependent chain
+template <class F>
+__device__ __noinline__ XYZZ<F> quad_scalar_mul(const XYZZ<F>& p, const uint64_t k[4]) {
+    XYZZ<F> tbl[16];
+    tbl[0] = XYZZ<F>::inf();
+    tbl[1] = p;
+    for (int i = 2; i < 16; i++) tbl[i] = quad_add(tbl[i - 1], p);
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int w = 63; w >= 0; w--) {
+        for (int j = 0; j < 4; j++) acc = quad_dbl(acc);
+        uint32_t d = (uint32_t)(k[w >> 4] >> ((w & 15) * 4)) & 15u;
+        if (d) acc = quad_add(acc, tbl[d]);
+    }
+    return acc;
+}
+
 // Fixed-base table T[w][d] = d * 16^w * G  (w < 64, d < 16), then out[i] = sum_w T[w][digit_w(k_i)]
 template <class F>
 __global__ void k_fixed_table(const Affine<F>* gen, XYZZ<F>* tbl) {
@@ -200,16 +216,20 @@ k_prove_finish_ab(const Jacobian<typename Curve::Fq>* jacA, const Jacobian<typen
     using Fq = typename Curve::Fq;
     const uint32_t p = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane != 0) return;
+    if (lane >= 4) return;                      // one quad per scalar multiplication
     if (warp == 0) {
         XYZZ<Fq> a = jacA[p].to_xyzz();
         auto s = s_all[p].from_mont();
-        sab[2 * p] = scalar_mul<Fq>(a, s.r.v);
-        outA_all[p] = a.to_affine();
-        inf_all[3 * p + 0] = a.is_inf() ? 1 : 0;
+        XYZZ<Fq> sa = quad_scalar_mul<Fq>(a, s.r.v);
+        if (lane == 0) {
+            sab[2 * p] = sa;
+            outA_all[p] = a.to_affine();
+            inf_all[3 * p + 0] = a.is_inf() ? 1 : 0;
+        }
     } else {
         auto r = r_all[p].from_mont();
-        sab[2 * p + 1] = scalar_mul<Fq>(jacB1[p].to_xyzz(), r.r.v);
+        XYZZ<Fq> rb = quad_scalar_mul<Fq>(jacB1[p].to_xyzz(), r.r.v);
+        if (lane == 0) sab[2 * p + 1] = rb;
     }
 }
 
