@@ -156,6 +156,19 @@ def workload_string(shape, wl, curve):
             f"bit-heavy witnesses")
 
 
+def make_config(args, wl, world, batch):
+    """The `config` object of BOTH arms (the reference arm is timed "on your arm's config", so it prints the same
+    dict): the workload, how the job is laid out over the GPUs, and why no L2 flush is needed."""
+    inflight = max(1, args.inflight)
+    return {"workload": workload_string(args.shape, wl, args.curve),
+            "subcircuits_per_gpu_per_step": batch, "global_batch": batch * world,
+            "parallelism": f"subcircuits sharded over {world} GPU(s), no data-path collective; protocol order per run: "
+                           f"all stage-0 commitments -> all_gather + host read-back (stage barrier, node.rs:488-539) -> "
+                           f"all stage-1 proofs -> all_gather; {inflight} batch(es) in flight per GPU within a phase "
+                           f"(hk_commit_batch / hk_prove_batch on forked contexts)",
+            "l2": "working set (resident window tables ~3 GB + MSM workspaces) exceeds the 126 MB L2: no flush needed"}
+
+
 # ------------------------------------------------------------------------------------------------------------
 class ShapeBench:
     """One subcircuit shape on one GPU: workload, resident proving key, per-pipeline contexts and buffers, and the
@@ -185,9 +198,17 @@ class ShapeBench:
             ps, cs = torch.cuda.Stream(device=local), torch.cuda.Stream(device=local)
             self.pipes.append(dict(pstream=ps, cstream=cs, ctx=ctx.fork(stream=ps.cuda_stream),
                                    cctx=ctx.fork(stream=cs.cuda_stream)))
-        self.all_ctxs = [c_ for pp in self.pipes for c_ in (pp["ctx"], pp["cctx"])]
+        # Phase A is latency-bound (a commitment MSM has a few dozen points): the K commitment batches of a run are
+        # independent, so they go to up to 8 commitment contexts and run side by side instead of queueing behind each
+        # other on two (3.1 -> ~1 ms for the phase at K = 6..8)
+        for _ in range(min(max(max_steps, inflight), 8) - inflight):
+            cs = torch.cuda.Stream(device=local)
+            self.pipes.append(dict(pstream=None, cstream=cs, ctx=None, cctx=ctx.fork(stream=cs.cuda_stream)))
+        self.cpipes = self.pipes                      # every entry has a commitment context
+        self.pipes = self.pipes[:inflight]            # the proof pipelines
+        self.all_ctxs = [pp["ctx"] for pp in self.pipes] + [pp["cctx"] for pp in self.cpipes]
         self.pstreams = [pp["pstream"] for pp in self.pipes]
-        self.cstreams = [pp["cstream"] for pp in self.pipes]
+        self.cstreams = [pp["cstream"] for pp in self.cpipes]
         # inputs: pinned host copies (e2e) and device copies (device-resident run)
         its = self.items
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).pin_memory()
@@ -245,8 +266,8 @@ class ShapeBench:
             s_.wait_stream(self.stream)
         for i in range(steps):                               # phase A: stage 0 (committer.rs:55-98)
             pc = self.d_coms[i % self.nout].data_ptr()
-            self.pipes[i % self.inflight]["cctx"].commit_batch_device(self.pk.handle, 0, b, self.dz.data_ptr(), m,
-                                                                      q + 64 * b, pc, pc + b * P1)
+            self.cpipes[i % len(self.cpipes)]["cctx"].commit_batch_device(self.pk.handle, 0, b, self.dz.data_ptr(), m,
+                                                                          q + 64 * b, pc, pc + b * P1)
         self._barrier_device(steps)
         for i in range(steps):                               # phase B: stage 1 (committer.rs:100-122)
             p = self.d_proofs[i % self.nout].data_ptr()
@@ -275,8 +296,8 @@ class ShapeBench:
             s_.wait_stream(self.stream)
         for i in range(steps):
             o = self.hout[i % self.nout]
-            self.pipes[i % self.inflight]["cctx"].commit_batch_async(self.pk.handle, 0, self.hz, self.hk, o["com"], o["cinf"])
-        for pp in self.pipes:
+            self.cpipes[i % len(self.cpipes)]["cctx"].commit_batch_async(self.pk.handle, 0, self.hz, self.hk, o["com"], o["cinf"])
+        for pp in self.cpipes:
             pp["cctx"].sync()                                # commitments are in host memory
         n = min(steps, self.nout)
         self.challenge = derive_stage1_requests(self._exchange_host([self.hout[i]["com"] for i in range(n)]))
@@ -564,8 +585,7 @@ def reference_arm(args):
     ok = a_pt == G1.mul(G1.mul(G1.gen, td["g1"]), exp["A"])
     sample = (f"{conc} subcircuit(s) (commit + prove) of the {batch}-subcircuit step per timed step, run concurrently "
               f"on pools of {pool} thread(s) each (node.rs:745-795)")
-    config = {"workload": workload_string(args.shape, wl, args.curve),
-              "subcircuits_per_gpu_per_step": batch, "global_batch": batch * args.gpus}
+    config = make_config(args, wl, max(1, args.gpus), batch)       # our arm's config, verbatim
     emit({
         "impl": "reference", "metric": "subcircuit proofs/s", "value": v, "unit": "proofs/s", "n_gpus": 0,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3,
@@ -680,13 +700,7 @@ def main():
     sb = ShapeBench(ctx, stream, args.shape, batch, inflight, max(args.steps, args.warmup), rank, world, local)
     wl = sb.wl
     assert len(shard_range(batch * world, world, rank)) == batch      # contiguous chunk per rank (node.rs:471-493)
-    config = {"workload": workload_string(args.shape, wl, args.curve),
-              "subcircuits_per_gpu_per_step": batch, "global_batch": batch * world,
-              "parallelism": f"subcircuits sharded over {world} GPU(s), no data-path collective; protocol order per run: "
-                             f"all stage-0 commitments -> all_gather + host read-back (stage barrier, node.rs:488-539) -> "
-                             f"all stage-1 proofs -> all_gather; {inflight} batch(es) in flight per GPU within a phase "
-                             f"(hk_commit_batch / hk_prove_batch on forked contexts)",
-              "l2": "working set (resident window tables ~3 GB + MSM workspaces) exceeds the 126 MB L2"}
+    config = make_config(args, wl, world, batch)
 
     verified = sb.verify_against_trapdoor()
     imad_peak = ctx.bench_imad_wide(8192)          # wide multiply-accumulates / s (roofline denominator)
