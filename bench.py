@@ -372,6 +372,14 @@ class ShapeBench:
         a0, b0, c0 = self.proof0
         return bool(np.array_equal(A, a0) and np.array_equal(Bp, b0) and np.array_equal(Cp, c0))
 
+    def host_outputs_match_single(self, step=0):
+        """After run_host: the page-locked output block of `step` holds, for proof 0, the blocking single call's
+        A, B, C (the end-to-end path produces the verified results too)."""
+        o = self.hout[step % self.nout]
+        a0, b0, c0 = self.proof0
+        return bool(np.array_equal(o["a"][0], a0) and np.array_equal(o["b"][0], b0) and np.array_equal(o["c"][0], c0)
+                    and not o["inf"].any() and not o["cinf"].any())
+
     def close(self):
         for c_ in self.all_ctxs:
             c_.close()
@@ -746,6 +754,7 @@ def main():
     # end to end through the host-buffer C-ABI calls
     sb.run_host(min(args.warmup, 2) * inflight)
     ms_e2e = run_timed(sb.run_host, args.steps)
+    e2e_same = sb.host_outputs_match_single(0)
     clocks = sampler.stop() if sampler else None
     sb.run_host_pageable(inflight)
     ms_pageable = timed_wall(torch, dist, dev, world, sb.run_host_pageable, args.steps)
@@ -853,6 +862,7 @@ def main():
                                             "thread(s), wall clock"}},
             "gpu_launches": launches, "roofline": roof, "roofline_ntt": roof_ntt, "cpu_baseline": cpu, "extras": extras,
             "setup_s": round(sb.setup_s, 1), "verified_vs_trapdoor": verified, "batch_equals_single_call": same_as_single,
+            "e2e_equals_single_call": e2e_same,
         }
         emit(line)
     sb.close()
