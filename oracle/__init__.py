@@ -24,7 +24,10 @@ What the oracle IS pinned against (tests/test_oracle_*.py):
   * RFC 7539 / ECRYPT ChaCha block vectors and the zcash-format BLS12-381
     generator encodings for the host-side RNG and serialisers
     (tests/test_rng.py, tests/test_serialize.py);
-  * an MSM/NTT-free trapdoor known-answer for whole proofs (cpgroth16.py).
+  * an MSM/NTT-free trapdoor known-answer for whole proofs (cpgroth16.py);
+  * the reference's own two acceptance tests (cp-groth16/src/lib.rs:139-180,
+    273-313) restated on its PolyEvalCircuit (reference_circuits.py,
+    tests/test_reference_poly_commit.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this package.  The product (hekaton_system_b200)
