@@ -106,6 +106,15 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def wait_first(self, timeout=5.0):
+        """Block until nvidia-smi has printed its first sample: its start-up (NVML initialisation on the GPU under test)
+        stalls kernel launches for ~100 ms -- seen once as a 43 ms/step outlier when it overlapped the timed region."""
+        t0 = time.time()
+        while self.p is not None and self.p.poll() is None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.02)
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -713,8 +722,12 @@ def main():
     verified = sb.verify_against_trapdoor()
     imad_peak = ctx.bench_imad_wide(8192)          # wide multiply-accumulates / s (roofline denominator)
 
+    # started before the warm-up so that its start-up cost never lands in the timed region; samples every 100 ms
+    sampler = ClockSampler(local) if rank == 0 and not args.timeline else None
     sb.run_device(args.warmup)
     torch.cuda.synchronize()
+    if sampler:
+        sampler.wait_first()
     if args.timeline:
         from torch.profiler import ProfilerActivity, profile
         nrun = 3 * inflight                       # steady state: the middle third is what tools/timeline_stats.py reads
@@ -743,7 +756,6 @@ def main():
         ctx.close()
         return 0
 
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = sum(c_.launches for c_ in sb.all_ctxs)
     ms_dev = run_timed(sb.run_device, args.steps)
     launches = sum(c_.launches for c_ in sb.all_ctxs) - l0

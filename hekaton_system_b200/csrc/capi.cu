@@ -437,7 +437,10 @@ HK_EXPORT int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value
                 ctx->opt_reduce_g = (uint32_t)value;
                 break;
             case HK_OPT_SORT_GLOBAL_ATOMICS: ctx->opt_sort_global = value ? 1u : 0u; break;
-            case HK_OPT_G2_LANE_PAIR: ctx->opt_g2_pair = value ? 1u : 0u; break;
+            case HK_OPT_G2_LANE_PAIR:
+                HK_REQUIRE(value <= 2, HK_ERR_INVALID, "HK_OPT_G2_LANE_PAIR must be 0 (auto), 1 (always) or 2 (never)");
+                ctx->opt_g2_pair = (uint32_t)value;
+                break;
             case HK_OPT_QUAD_MAX_THREADS:
                 HK_REQUIRE(value <= (1u << 24), HK_ERR_INVALID, "HK_OPT_QUAD_MAX_THREADS must be 0..2^24");
                 ctx->opt_quad_max = (uint32_t)value;

@@ -246,6 +246,7 @@ def test_scalar_mul_matches_oracle(ctx, group):
     {B.OPT_ACCUM_WAVES: 64, B.OPT_ACCUM_SEG_MIN: 3, B.OPT_FOLD_SEG: 8, B.OPT_REDUCE_CHUNK: 1},
     {B.OPT_SORT_GLOBAL_ATOMICS: 1},                                   # table sets through the global-atomic sort
     {B.OPT_G2_LANE_PAIR: 1, B.OPT_ACCUM_SEG_MIN: 5},                  # Fq2 values spread over lane pairs (BLS12-381 G2)
+    {B.OPT_G2_LANE_PAIR: 2, B.OPT_ACCUM_SEG_MIN: 7},                  # ... and never: one thread per G2 addition
     {B.OPT_QUAD_MAX_THREADS: 1, B.OPT_ACCUM_SEG_MIN: 2},              # no quad-cooperative tail kernels at all
     {B.OPT_QUAD_MAX_THREADS: 1 << 24, B.OPT_ACCUM_SEG_MIN: 2, B.OPT_FOLD_SEG: 8},   # every tail kernel quad-cooperative
 ])

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Run a few MSMs (window-table mode) -- target for ncu captures.
-usage: msm_once.py LOG_N REPS GROUP KIND(uniform|witness) K DENSITY"""
+usage: msm_once.py LOG_N REPS GROUP KIND(uniform|witness) K DENSITY      (HK_PROBE_OPTS="g2pair=1,smin=32": hk_ctx_set_option knobs)"""
 import os
 import sys
 
@@ -20,6 +20,9 @@ density = float(sys.argv[6]) if len(sys.argv) > 6 else 1.0
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 ctx = Context("bls12_381", 0, stream=stream.cuda_stream)
+for kv in filter(None, os.environ.get("HK_PROBE_OPTS", "").split(",")):
+    from msm_time_names import NAMES
+    ctx.set_option(NAMES[kv.split("=")[0]], int(kv.split("=")[1]))
 cv = ctx.curve
 n = 1 << lg
 rng = np.random.default_rng(1)

@@ -14,7 +14,7 @@ from hekaton_system_b200 import codec
 from hekaton_system_b200.backend import Context
 from sweep import best_ms, limb_dot_mod
 
-NAMES = {"waves": B.OPT_ACCUM_WAVES, "smin": B.OPT_ACCUM_SEG_MIN, "fold": B.OPT_FOLD_SEG, "chunk": B.OPT_REDUCE_CHUNK, "gsort": B.OPT_SORT_GLOBAL_ATOMICS, "g2pair": B.OPT_G2_LANE_PAIR, "quad": B.OPT_QUAD_MAX_THREADS}
+from msm_time_names import NAMES
 
 group = int(sys.argv[1])
 sizes = [int(x) for x in sys.argv[2].split(",")]
