@@ -61,7 +61,7 @@ def parse():
                     help="proof batches in flight per GPU: step i runs on pipeline i %% inflight (own contexts, streams and "
                          "scratch), so the latency-bound tail of one batch overlaps the head of the next")
     ap.add_argument("--opt", action="append", default=[],
-                    help="MSM tuning knob for A/B runs, name=value with name in waves|smin|fold|chunk|gsort|g2pair|quad "
+                    help="MSM tuning knob for A/B runs, name=value with name in waves|smin|fold|chunk|gsort|g2pair|quad|noresolve "
                          "(hk_ctx_set_option; results never depend on them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the standalone MSM / NTT measurements and the other shapes")
@@ -704,7 +704,7 @@ def main():
     ctx = Context(args.curve, device=local, stream=stream.cuda_stream)
     if args.opt:
         names = {"waves": hk_backend.OPT_ACCUM_WAVES, "smin": hk_backend.OPT_ACCUM_SEG_MIN, "fold": hk_backend.OPT_FOLD_SEG,
-                 "chunk": hk_backend.OPT_REDUCE_CHUNK, "gsort": hk_backend.OPT_SORT_GLOBAL_ATOMICS, "g2pair": hk_backend.OPT_G2_LANE_PAIR, "quad": hk_backend.OPT_QUAD_MAX_THREADS}
+                 "chunk": hk_backend.OPT_REDUCE_CHUNK, "gsort": hk_backend.OPT_SORT_GLOBAL_ATOMICS, "g2pair": hk_backend.OPT_G2_LANE_PAIR, "quad": hk_backend.OPT_QUAD_MAX_THREADS, "noresolve": hk_backend.OPT_NO_FOLD_RESOLVE}
         for kv in args.opt:
             k_, v_ = kv.split("=")
             ctx.set_option(names[k_], int(v_))         # forks inherit the settings

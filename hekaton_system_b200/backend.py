@@ -14,7 +14,7 @@ from .curves import get_curve
 HK_HOST, HK_DEVICE, HK_HOST_PINNED, HK_HOST_PINNED_ASYNC = 0, 1, 2, 3
 SCALAR_BIGINT, SCALAR_MONT = 0, 1
 NTT_FORWARD, NTT_INVERSE = 0, 1
-OPT_ACCUM_WAVES, OPT_ACCUM_SEG_MIN, OPT_FOLD_SEG, OPT_REDUCE_CHUNK, OPT_SORT_GLOBAL_ATOMICS, OPT_G2_LANE_PAIR, OPT_QUAD_MAX_THREADS = 1, 2, 3, 4, 5, 6, 7
+OPT_ACCUM_WAVES, OPT_ACCUM_SEG_MIN, OPT_FOLD_SEG, OPT_REDUCE_CHUNK, OPT_SORT_GLOBAL_ATOMICS, OPT_G2_LANE_PAIR, OPT_QUAD_MAX_THREADS, OPT_NO_FOLD_RESOLVE = 1, 2, 3, 4, 5, 6, 7, 8
 DOMAIN_PLAIN, DOMAIN_COSET = 0, 1
 FIELD_FR, FIELD_FQ, FIELD_FQ2 = 0, 1, 2
 (FOP_MUL, FOP_ADD, FOP_SUB, FOP_INV, FOP_TO_MONT, FOP_FROM_MONT, FOP_INV_GCD, FOP_SQR, FOP_MUL_KARA,

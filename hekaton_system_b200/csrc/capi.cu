@@ -393,6 +393,7 @@ HK_EXPORT int32_t hk_ctx_fork(hk_ctx* parent, void* stream, hk_ctx** out) {
     ctx->opt_sort_global = parent->opt_sort_global;
     ctx->opt_g2_pair = parent->opt_g2_pair;
     ctx->opt_quad_max = parent->opt_quad_max;
+    ctx->opt_no_fold_resolve = parent->opt_no_fold_resolve;
     if (cudaSetDevice(ctx->device) != cudaSuccess) {
         delete ctx;
         return HK_ERR_CUDA;
@@ -445,6 +446,7 @@ HK_EXPORT int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value
                 HK_REQUIRE(value <= (1u << 24), HK_ERR_INVALID, "HK_OPT_QUAD_MAX_THREADS must be 0..2^24");
                 ctx->opt_quad_max = (uint32_t)value;
                 break;
+            case HK_OPT_NO_FOLD_RESOLVE: ctx->opt_no_fold_resolve = value ? 1u : 0u; break;
             default: throw HkError{HK_ERR_INVALID, "unknown option"};
         }
     });

@@ -221,7 +221,7 @@ struct hk_ctx {
     // at a time and the profiling events bracket each kernel alone (roofline measurements)
     bool serial_lanes = false;
     // MSM tuning knobs (hk_ctx_set_option; 0 = built-in default, see msm_accumulate)
-    uint32_t opt_accum_waves = 0, opt_accum_smin = 0, opt_fold_seg = 0, opt_reduce_g = 0, opt_sort_global = 0, opt_g2_pair = 0, opt_quad_max = 0;
+    uint32_t opt_accum_waves = 0, opt_accum_smin = 0, opt_fold_seg = 0, opt_reduce_g = 0, opt_sort_global = 0, opt_g2_pair = 0, opt_quad_max = 0, opt_no_fold_resolve = 0;
     cudaStream_t lane_stream(int lane) const { return !serial_lanes && lane > 0 && lane < LANES ? lane_ctl[lane] : stream; }
     cudaStream_t bulk_stream(int lane) const { return !serial_lanes && lane > 0 && lane < LANES ? lane_bulk[lane] : stream; }
     // stream used by the NTT / QAP kernels (normally the main stream; prove_run points it at the H lane)

@@ -554,11 +554,13 @@ k_msm_tree_sum(const XYZZ<F>* __restrict__ in, uint32_t m, uint32_t in_stride, X
 template <class F, int S>
 __global__ void __launch_bounds__(128)
 k_msm_fold_quad(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys, uint32_t n_in,
-                XYZZ<F>* buckets, XYZZ<F>* out, uint32_t* out_keys, uint32_t nthreads, int final_level) {
+                XYZZ<F>* buckets, XYZZ<F>* out, uint32_t* out_keys, uint32_t nthreads, int final_level,
+                const uint32_t* __restrict__ gate) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t t = g >> 2;
     const bool lead = (g & 3u) == 0;
     if (t >= nthreads) return;
+    if (gate != nullptr && *gate == 0) return;     // k_msm_fold_resolve_quad has already finished the list
     size_t lo = (size_t)t * S;
     size_t hi = lo + S < n_in ? lo + S : n_in;
     uint32_t cur = KEY_NONE, first_key = KEY_NONE;
@@ -598,6 +600,77 @@ k_msm_fold_quad(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_
     if (!final_level && lead) {
         out_keys[2 * (size_t)t] = k0;
         out_keys[2 * (size_t)t + 1] = k1;
+    }
+}
+
+// ---- all remaining borders at once ------------------------------------------------------------------------
+// A partial list holds, per producer thread i, the sum of the first run of its range (slot 2i, "F_i") and of its last
+// run (slot 2i+1, "L_i", absent when the whole range was one run); keys never decrease along the list.  The level-by-
+// level fold pairs L_i with F_{i+1} only at the level whose segments swallow border i -- log2(threads) launches, each
+// one dependent addition long.  Once a thread's range is longer than any bucket's run, every run of equal keys in the
+// list has at most two pieces (L_i, F_{i+1}) and ALL borders can be closed in one launch: fold_runs classifies the (at
+// most two) runs that start in thread i's slots; k_msm_fold_check raises a flag if any run has three or more pieces
+// (a thread whose whole range lies inside one bucket's run: skewed scalars) or if the list has a hole before its end;
+// k_msm_fold_resolve_quad closes every run when the flag is clear, and the remaining fold levels return at once
+// (`gate`).  With the flag set nothing is written and the levels run as before.
+struct FoldRuns {
+    bool a, a_merge, b, b_merge, bad;      // run A starts at F_i (pieces F_i [, F_{i+1}]); run B at L_i ([, F_{i+1}])
+    uint32_t ka, kb;
+};
+
+__device__ __forceinline__ FoldRuns fold_runs(const uint32_t* __restrict__ keys, uint32_t i, uint32_t n) {
+    FoldRuns r{false, false, false, false, false, KEY_NONE, KEY_NONE};
+    const uint32_t k0 = keys[2 * i], k1 = keys[2 * i + 1];
+    const uint32_t nk0 = i + 1 < n ? keys[2 * i + 2] : KEY_NONE, nk1 = i + 1 < n ? keys[2 * i + 3] : KEY_NONE;
+    if (k0 == KEY_NONE) {                  // empty thread: legal only past the end of the list
+        r.bad = (k1 != KEY_NONE) || (nk0 != KEY_NONE);
+        return r;
+    }
+    uint32_t prev = KEY_NONE;              // key of the piece in front of F_i
+    if (i > 0) {
+        prev = keys[2 * i - 1];
+        if (prev == KEY_NONE) prev = keys[2 * i - 2];
+    }
+    const uint32_t nnk0 = i + 2 < n ? keys[2 * i + 4] : KEY_NONE;
+    const bool next_single = nk0 != KEY_NONE && nk1 == KEY_NONE;      // thread i+1 holds one piece only
+    r.ka = k0;
+    r.kb = k1;
+    if (k1 != KEY_NONE) {
+        r.a = prev != k0;                  // F_i alone (L_i has another key)
+        r.b = true;
+        r.b_merge = nk0 == k1;
+        r.bad = r.b_merge && next_single && nnk0 == k1;
+    } else if (prev != k0) {
+        r.a = true;
+        r.a_merge = nk0 == k0;
+        r.bad = r.a_merge && next_single && nnk0 == k0;
+    }
+    return r;
+}
+
+static __global__ void k_msm_fold_check(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (fold_runs(keys, i, n).bad) *flag = 1u;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+k_msm_fold_resolve_quad(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ keys, uint32_t n,
+                        XYZZ<F>* buckets, const uint32_t* __restrict__ flag) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = g >> 2;
+    const bool lead = (g & 3u) == 0;
+    if (i >= n || *flag != 0) return;
+    const FoldRuns r = fold_runs(keys, i, n);
+#pragma unroll 1
+    for (int run = 0; run < 2; run++) {    // one quad_add call site: quads of a warp that diverge here still share it
+        const bool have = run == 0 ? r.b : r.a;
+        if (!have) continue;
+        const bool merge = run == 0 ? r.b_merge : r.a_merge;
+        XYZZ<F> acc = in[2 * (size_t)i + (run == 0 ? 1 : 0)];
+        if (merge) acc = quad_add(acc, in[2 * (size_t)i + 2]);
+        if (lead) buckets[run == 0 ? r.kb : r.ka] = acc;
     }
 }
 
@@ -869,7 +942,8 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     }
     size_t part_total = 0;
     for (uint32_t v : lvl_in) part_total += v;
-    XYZZ<F>* buckets = ws.buckets.as<XYZZ<F>>(nkeys);
+    XYZZ<F>* buckets = ws.buckets.as<XYZZ<F>>(nkeys + 1);      // + the fold's "runs left" flag, cleared with the buckets
+    uint32_t* d_fold_flag = reinterpret_cast<uint32_t*>(buckets + nkeys);
     XYZZ<F>* partial = ws.chunks.as<XYZZ<F>>(part_total);
     uint32_t* partial_keys = ws.misc.as<uint32_t>(part_total);
     // reduction geometry: short serial chunks, then a multi-block tree
@@ -889,7 +963,7 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     for (uint32_t m : tree) tree_total += (size_t)ceil_div(m, 2 * TS_TPB) * nsets;
     XYZZ<F>* chunk_out = ws.wsum.as<XYZZ<F>>(tree_total + nsets);
 
-    HK_CUDA(cudaMemsetAsync(buckets, 0, nkeys * sizeof(XYZZ<F>), st));
+    HK_CUDA(cudaMemsetAsync(buckets, 0, (nkeys + 1) * sizeof(XYZZ<F>), st));
     // the accumulation needs the sorted list (possibly another lane's) and this lane's cleared buckets
     if (sb != st) {
         HK_CUDA(cudaEventRecord(ctx->ev_ready[lane], st));
@@ -924,6 +998,18 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
         HK_CUDA(cudaEventRecord(ctx->ev_accum[lane], sb));
         HK_CUDA(cudaStreamWaitEvent(st, ctx->ev_accum[lane], 0));
     }
+    // Where a thread's range (s_min items, times S1 / 2 per level) has grown past 1.5 x the longest run expected of a
+    // bucket and the list is short enough for the quad kernels, all borders are closed at once (k_msm_fold_resolve_quad)
+    // and the remaining levels are gated off; skewed inputs fail the check and fold level by level as before.
+    // Standalone G1 2^16: 11 launches of ~12.5 us -> 2 + 11 empty ones.
+    // expected longest run of a bucket for uniform scalars: n / 2^(c-1) items per full window, and the top window
+    // (t = bits - c (W - 1) bits wide) piles its n digits onto 2^(t-1) buckets; all windows share the buckets of a table
+    const double n_vec = double(so.max_items) / double(K * (size_t)pl.W);
+    const int top_bits = (int)Curve::FR_BITS - pl.c * (pl.W - 1);
+    const double run_full = n_vec / double(pl.B), run_top = n_vec / double(1u << (top_bits > 1 ? (top_bits < pl.c ? top_bits - 1 : pl.c - 1) : 0));
+    const double long_run = so.table ? (pl.W - 1) * run_full + run_top : (run_full > run_top ? run_full : run_top);
+    double range = double(s_min);
+    bool resolved = false;
     size_t off = 0;
     for (size_t l = 0; l < lvl_in.size(); l++) {
         uint32_t n_in = lvl_in[l];
@@ -933,10 +1019,21 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
         uint32_t* in_keys = partial_keys + off;
         XYZZ<F>* out = partial + off + n_in;
         uint32_t* out_keys = partial_keys + off + n_in;
+        if (!resolved && !final_level && !ctx->opt_no_fold_resolve && n_in / 2 <= quad_max && thr <= quad_max &&
+            range >= 1.5 * long_run) {
+            const uint32_t n = n_in / 2;
+            k_msm_fold_check<<<ceil_div(n, 256), 256, 0, st>>>(in_keys, n, d_fold_flag);
+            HK_LAUNCH_CHECK(ctx);
+            k_msm_fold_resolve_quad<F><<<ceil_div(4 * (size_t)n, 128), 128, 0, st>>>(in, in_keys, n, buckets, d_fold_flag);
+            HK_LAUNCH_CHECK(ctx);
+            resolved = true;
+        }
+        range *= double(S1 / 2);
+        const uint32_t* gate = resolved ? d_fold_flag : nullptr;
 #define HK_FOLD(SS)                                                                                                      \
     do {                                                                                                                \
         if (thr <= quad_max)                                                                                            \
-            k_msm_fold_quad<F, SS><<<ceil_div(4 * (size_t)thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level); \
+            k_msm_fold_quad<F, SS><<<ceil_div(4 * (size_t)thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level, gate); \
         else                                                                                                            \
             k_msm_fold<F, SS, 1><<<ceil_div(thr, 128), 128, 0, st>>>(in, in_keys, n_in, buckets, out, out_keys, thr, final_level); \
     } while (0)

@@ -55,7 +55,7 @@ static constexpr uint32_t NTT_TMAX = 11;   // tile = 2^11 elements = 64 KiB of s
 static constexpr uint32_t NTT_QMAX = 2;
 static constexpr uint32_t NTT_TPB = 256;   // one radix-8 group per thread and round on a full tile
 
-enum : uint32_t { NTT_PERM_IN = 1, NTT_PERM_OUT = 2, NTT_TOP_PASS = 4 };
+enum : uint32_t { NTT_PERM_IN = 1, NTT_PERM_OUT = 2, NTT_TOP_PASS = 4, NTT_RMAX_SHIFT = 4 };   // bits 4-5: stages per round (0 = 3)
 
 struct NttDomain {
     uint32_t log_n = 0;
@@ -83,28 +83,46 @@ struct NttPass {
 static constexpr uint32_t NTT_TOP_MIN = 21;
 static constexpr uint32_t NTT_TOP_BITS = 2;
 
-inline std::vector<NttPass> ntt_plan(uint32_t log_n, bool perm = false) {
+inline std::vector<NttPass> ntt_plan(uint32_t log_n, bool perm = false, uint32_t tmax = NTT_TMAX) {
     std::vector<NttPass> p;
     if (log_n == 0) return p;
-    if (log_n <= NTT_TMAX) {
+    if (log_n <= tmax) {
         p.push_back({0, log_n, 0, log_n});
         return p;
     }
     const bool top = perm && log_n >= NTT_TOP_MIN;
-    uint32_t last = top ? NTT_TMAX - NTT_TOP_BITS : NTT_TMAX;
+    uint32_t last = top ? tmax - NTT_TOP_BITS : tmax;
     uint32_t rest = log_n - last;
-    uint32_t per = NTT_TMAX - NTT_QMAX;
+    uint32_t per = tmax - NTT_QMAX;
     uint32_t np = (rest + per - 1) / per;
     uint32_t s = 0;
     for (uint32_t i = 0; i < np; i++) {
         uint32_t k = rest / np + (i < rest % np ? 1 : 0);
         uint32_t L = log_n - s - k;
         uint32_t q = L < NTT_QMAX ? L : NTT_QMAX;
-        p.push_back({s, k, q, NTT_TMAX});
+        p.push_back({s, k, q, tmax});
         s += k;
     }
-    p.push_back({s, last, 0, NTT_TMAX});
+    p.push_back({s, last, 0, tmax});
     return p;
+}
+
+// Tile size for K transforms of 2^log_n elements.  A pass is one CTA per tile, and a CTA walks its tile's stages in
+// sequence (~40 us for 11 stages on 2^11 elements), so a grid that cannot fill the 148 SMs is pure latency: a single
+// 2^16 transform is 32 tiles.  When 2^11-element tiles give fewer than two CTAs per SM, take the smallest tile
+// (down to 2^9) that needs no more passes: 2^16 -> 2^9 (128 tiles), 2^17 / 2^18 -> 2^10.  Such a pass also runs
+// fewer stages per register round (1 on 2^9 tiles, 2 on 2^10) with 256 threads: a radix-8 round is 12 multiplications
+// per thread in three dependent steps, a radix-2 round one -- the chain a lone warp walks is what such a launch costs.
+inline uint32_t ntt_tile_bits(uint32_t log_n, size_t K, int sm_count) {
+    if (log_n <= 9 || log_n >= NTT_TOP_MIN) return NTT_TMAX;
+    const size_t tiles = log_n > NTT_TMAX ? (K << (log_n - NTT_TMAX)) : K;
+    if (tiles >= (size_t)2 * sm_count) return NTT_TMAX;
+    auto passes = [log_n](uint32_t t) -> uint32_t {
+        return log_n <= t ? 1u : 1u + (log_n - t + (t - NTT_QMAX) - 1) / (t - NTT_QMAX);
+    };
+    uint32_t t = NTT_TMAX;
+    while (t > 9 && passes(t - 1) == passes(NTT_TMAX)) t--;
+    return t;
 }
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return bits ? (__brev(x) >> (32 - bits)) : 0; }
@@ -232,9 +250,10 @@ k_ntt_pass(const Fr* in_all, Fr* out_all, const Fr* __restrict__ tw, uint32_t lo
 
     // the k stages act on tile bits [q, q + k): DIF from the top bit down, DIT from the bottom bit up,
     // three bits (one radix-8 round) at a time
+    const uint32_t rmax = ((flags >> NTT_RMAX_SHIFT) & 3u) ? ((flags >> NTT_RMAX_SHIFT) & 3u) : 3u;
     uint32_t done = 0;
     while (done < k) {
-        const uint32_t R = (k - done >= 3) ? 3 : (k - done);
+        const uint32_t R = (k - done >= rmax) ? rmax : (k - done);
         const uint32_t pos_lo = DIT ? (q + done) : (q + k - done - R);
         if (R == 3) ntt_round<Fr, DIT, 3>(slo, shi, tw, N, gidx, s0, tile, pos_lo);
         else if (R == 2) ntt_round<Fr, DIT, 2>(slo, shi, tw, N, gidx, s0, tile, pos_lo);
@@ -394,7 +413,10 @@ void ntt_passes(hk_ctx* ctx, const NttDomain& d, bool dit, bool inverse_root, co
     const uint32_t log_n = d.log_n;
     // the bit reversal sits on the L = 0 pass only for DIT + perm_in (first pass) and DIF + perm_out (last pass)
     const bool top_pass = ((dit && perm_in) || (!dit && perm_out)) && log_n >= NTT_TOP_MIN && log_n > NTT_TMAX;
-    auto plan = ntt_plan(log_n, top_pass);
+    const uint32_t tbits = ntt_tile_bits(log_n, K, ctx->sm_count);
+    auto plan = ntt_plan(log_n, top_pass, tbits);
+    const unsigned tpb = NTT_TPB;
+    const uint32_t rflag = tbits >= NTT_TMAX ? 0u : ((tbits - 8u) << NTT_RMAX_SHIFT);
     const Fr* tw = reinterpret_cast<const Fr*>(inverse_root ? d.tw_inv : d.tw_fwd);
     const size_t np = plan.size();
     if (dit) {
@@ -414,6 +436,7 @@ void ntt_passes(hk_ctx* ctx, const NttDomain& d, bool dit, bool inverse_root, co
         if (first && perm_in) flags |= NTT_PERM_IN;
         if (last && perm_out) flags |= NTT_PERM_OUT;
         if (top_pass && ps.s0 + ps.k == log_n) flags |= NTT_TOP_PASS;     // the L = 0 pass
+        flags |= rflag;
         const bool oop = (flags & (NTT_PERM_IN | NTT_PERM_OUT)) != 0;
         Fr* to;
         if (last) {
@@ -433,11 +456,11 @@ void ntt_passes(hk_ctx* ctx, const NttDomain& d, bool dit, bool inverse_root, co
         const Fr* pc = last ? post_const : nullptr;
         int pidx = prof_begin(ctx, HK_PROF_NTT_PASS, ctx->qstream());
         if (dit)
-            k_ntt_pass<Fr, true><<<grid, NTT_TPB, smem, ctx->qstream()>>>(cur, to, tw, log_n, ps.s0, ps.k, ps.q, ps.T, pre,
-                                                                       post, pc, flags);
+            k_ntt_pass<Fr, true><<<grid, tpb, smem, ctx->qstream()>>>(cur, to, tw, log_n, ps.s0, ps.k, ps.q, ps.T, pre,
+                                                                   post, pc, flags);
         else
-            k_ntt_pass<Fr, false><<<grid, NTT_TPB, smem, ctx->qstream()>>>(cur, to, tw, log_n, ps.s0, ps.k, ps.q, ps.T, pre,
-                                                                        post, pc, flags);
+            k_ntt_pass<Fr, false><<<grid, tpb, smem, ctx->qstream()>>>(cur, to, tw, log_n, ps.s0, ps.k, ps.q, ps.T, pre,
+                                                                    post, pc, flags);
         HK_LAUNCH_CHECK(ctx);
         prof_end(ctx, pidx, (uint64_t)K << log_n, nullptr, ctx->qstream());
         cur = to;

@@ -110,9 +110,14 @@ int32_t hk_ctx_destroy(hk_ctx* ctx);
  *                         0 = automatic (default: lists of up to 5 M items, i.e. window tables below ~1 GB, where it
  *                         measures 3-8 % faster), 1 = always, 2 = never (one thread per point addition)
  *   HK_OPT_QUAD_MAX_THREADS  fold / reduction / tree-sum launches of at most this many logical threads run with four
- *                         lanes per point addition (default 32768; 1 = never) */
+ *                         lanes per point addition (default 32768 for a standalone MSM, never inside a proof
+ *                         batch; 1 = never)
+ *   HK_OPT_NO_FOLD_RESOLVE  1 = fold the partial list level by level to the end (default 0: where the quad-cooperative
+ *                         kernels are in use and a thread's range has outgrown the bucket runs, one launch closes
+ *                         every border at once -- after a check that no run has more than two pieces -- and the
+ *                         remaining levels return immediately) */
 enum { HK_OPT_ACCUM_WAVES = 1, HK_OPT_ACCUM_SEG_MIN = 2, HK_OPT_FOLD_SEG = 3, HK_OPT_REDUCE_CHUNK = 4,
-       HK_OPT_SORT_GLOBAL_ATOMICS = 5, HK_OPT_G2_LANE_PAIR = 6, HK_OPT_QUAD_MAX_THREADS = 7 };
+       HK_OPT_SORT_GLOBAL_ATOMICS = 5, HK_OPT_G2_LANE_PAIR = 6, HK_OPT_QUAD_MAX_THREADS = 7, HK_OPT_NO_FOLD_RESOLVE = 8 };
 int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value);
 int32_t hk_ctx_sync(hk_ctx* ctx);
 const char* hk_last_error_string(hk_ctx* ctx);

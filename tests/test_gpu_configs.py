@@ -20,11 +20,12 @@ pytestmark = pytest.mark.gpu
 
 
 # ---------------------------------------------------------------------------------------- NTT
-@pytest.mark.parametrize("log_n", [16, 20, 21, 24])
+@pytest.mark.parametrize("log_n", [12, 14, 15, 16, 17, 18, 19, 20, 21, 24])
 def test_ntt_elementwise_vs_c_oracle(ctx, log_n):
     """Every output element of hk_ntt equals ark-poly's fft / ifft / coset fft / coset ifft as restated in C
     (in-order radix-2 with the bit reversal up front -- a different schedule from the device's tiled radix-8
-    passes).  2^21 and 2^24 exercise the 3-pass plans and the top-passenger tile."""
+    passes).  2^21 and 2^24 exercise the 3-pass plans and the top-passenger tile; 2^12 ... 2^18 the smaller tiles a
+    single transform gets when 2^11-element tiles could not fill the GPU (ntt_tile_bits)."""
     cv = ctx.curve
     n = 1 << log_n
     rng = np.random.default_rng(100 + log_n)
@@ -39,6 +40,23 @@ def test_ntt_elementwise_vs_c_oracle(ctx, log_n):
         ref = x.copy()
         cref.ntt(cv.cid, ref, log_n, inverse=inverse, coset=coset, threads=cref.max_threads())
         assert np.array_equal(got, ref), (log_n, inverse, coset)
+
+
+@pytest.mark.parametrize("log_n,K", [(13, 5), (16, 3), (16, 40)])
+def test_ntt_batch_elementwise_vs_c_oracle(ctx, log_n, K):
+    """K transforms in one call: small batches take the small tiles, large ones the 2^11-element tiles."""
+    cv = ctx.curve
+    n = 1 << log_n
+    rng = np.random.default_rng(7 * log_n + K)
+    x = rng.integers(0, 1 << 62, size=(K * n, 4), dtype=np.uint64)
+    x[:, 3] >>= 2
+    for inverse, coset in ((False, True), (True, False)):
+        got = x.copy()
+        ctx.ntt(got, log_n, inverse=inverse, coset=coset, K=K)
+        for k in range(K):
+            ref = x[k * n:(k + 1) * n].copy()
+            cref.ntt(cv.cid, ref, log_n, inverse=inverse, coset=coset, threads=cref.max_threads())
+            assert np.array_equal(got[k * n:(k + 1) * n], ref), (log_n, K, k, inverse, coset)
 
 
 @pytest.mark.parametrize("log_n", [16, 18])

@@ -249,6 +249,8 @@ def test_scalar_mul_matches_oracle(ctx, group):
     {B.OPT_G2_LANE_PAIR: 2, B.OPT_ACCUM_SEG_MIN: 7},                  # ... and never: one thread per G2 addition
     {B.OPT_QUAD_MAX_THREADS: 1, B.OPT_ACCUM_SEG_MIN: 2},              # no quad-cooperative tail kernels at all
     {B.OPT_QUAD_MAX_THREADS: 1 << 24, B.OPT_ACCUM_SEG_MIN: 2, B.OPT_FOLD_SEG: 8},   # every tail kernel quad-cooperative
+    {B.OPT_QUAD_MAX_THREADS: 1 << 24, B.OPT_NO_FOLD_RESOLVE: 1, B.OPT_ACCUM_SEG_MIN: 1},   # one launch per fold level to the end
+    {B.OPT_QUAD_MAX_THREADS: 1 << 24, B.OPT_ACCUM_SEG_MIN: 64, B.OPT_FOLD_SEG: 4},   # borders closed at once from the first level on
 ])
 def test_tuning_options_never_change_results(ctx, opts):
     """hk_ctx_set_option: the accumulation geometry (waves, minimum segment) and the fold / reduction chunking only
