@@ -977,11 +977,13 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     // (the one-thread kernel: 255 with 1 KB of spills), multiplier pipe 81.9 % vs 72.1 % busy in the `ncu --set full`
     // captures at 2^18 (profiles/r02p_*): 4.64 vs 5.16 ms.  Measured standalone (G2 MSM, ms, pair vs one thread):
     // 2^16 2.77 / 2.86, 2^17 4.40 / 4.73, 2^18 6.42 / 6.97, 2^19 11.42 / 11.36, 2^20 21.33 / 21.07 -- the gain is gone
-    // once the window table passes ~1 GB, so the default (HK_OPT_G2_LANE_PAIR = 0) picks it for lists of up to 5 M
-    // items (2^18 points x 16 windows: every proof shape but VM); 1 = always, 2 = never.  Proof pipeline: +1 %.
+    // once the window table passes ~1 GB, so the default (HK_OPT_G2_LANE_PAIR = 0) picks it for base sets of up to
+    // 5 M table entries (2^18 points x 16 windows: every proof shape but VM), whatever the batch; 1 = always,
+    // 2 = never.  Proof pipeline: +1 %.
     if constexpr (GROUP == 2) {
         if constexpr (F::base::HAS_MUL2) {
-            if (ctx->opt_g2_pair == 1 || (ctx->opt_g2_pair == 0 && so.max_items <= 5000000)) {
+            const size_t entries = so.table ? (size_t)bv.n_total * (size_t)pl.W : (size_t)bv.n_total;
+            if (ctx->opt_g2_pair == 1 || (ctx->opt_g2_pair == 0 && entries <= 5000000)) {
                 k_msm_accum_g2pair<F, 2><<<ceil_div(2 * (size_t)nthr0, 128), 128, 0, sb>>>(d_bases, so.pairs, so.d_count, s_min,
                                                                                         buckets, partial, partial_keys, nthr0);
                 launched = true;
