@@ -439,7 +439,7 @@ HK_EXPORT int32_t hk_ctx_set_option(hk_ctx* ctx, uint32_t option, uint64_t value
                 break;
             case HK_OPT_SORT_GLOBAL_ATOMICS: ctx->opt_sort_global = value ? 1u : 0u; break;
             case HK_OPT_G2_LANE_PAIR:
-                HK_REQUIRE(value <= 2, HK_ERR_INVALID, "HK_OPT_G2_LANE_PAIR must be 0 (auto), 1 (always) or 2 (never)");
+                HK_REQUIRE(value <= 2, HK_ERR_INVALID, "HK_OPT_G2_LANE_PAIR must be 0, 1 (on) or 2 (off)");
                 ctx->opt_g2_pair = (uint32_t)value;
                 break;
             case HK_OPT_QUAD_MAX_THREADS:

@@ -412,9 +412,25 @@ k_msm_accum_g2pair(const Affine<F2>* __restrict__ bases, const uint64_t* __restr
         const uint32_t first_key = cur;
         XYZZ<H> acc = XYZZ<H>::inf();
         bool first_done = false;
+        // software pipeline: the base of item i + 1 is in flight while item i is added (254 registers, no spills;
+        // -1 % at every size, which is what keeps this kernel level with the one-thread kernel on tables > 1 GB)
+        uint64_t pr = pairs[lo];
+        Affine<H> pn;
+        {
+            const Fb* src = reinterpret_cast<const Fb*>(bases + ((uint32_t)pr >> 1));
+            pn.x.v = src[0 + par];
+            pn.y.v = src[2 + par];
+        }
         for (size_t i = lo; i < hi; i++) {
-            const uint64_t pr = pairs[i];
             const uint32_t k = (uint32_t)(pr >> 32);
+            const uint32_t it = (uint32_t)pr;
+            const Affine<H> p = pn;
+            if (i + 1 < hi) {
+                pr = pairs[i + 1];
+                const Fb* src = reinterpret_cast<const Fb*>(bases + ((uint32_t)pr >> 1));
+                pn.x.v = src[0 + par];
+                pn.y.v = src[2 + par];
+            }
             if (k != cur) {
                 if (!first_done) {
                     store(&partial[2 * (size_t)t], acc);
@@ -425,11 +441,6 @@ k_msm_accum_g2pair(const Affine<F2>* __restrict__ bases, const uint64_t* __restr
                 acc = XYZZ<H>::inf();
                 cur = k;
             }
-            const uint32_t it = (uint32_t)pr;
-            const Fb* src = reinterpret_cast<const Fb*>(bases + (it >> 1));
-            Affine<H> p;
-            p.x.v = src[0 + par];
-            p.y.v = src[2 + par];
             acc.madd(p, it & 1);
         }
         k0 = first_key;
@@ -973,17 +984,14 @@ void msm_accumulate(hk_ctx* ctx, const MsmSorted& so, const MsmBases& bv, void* 
     int pi = prof_begin(ctx, GROUP == 1 ? HK_PROF_MSM_ACCUM_G1 : HK_PROF_MSM_ACCUM_G2, sb);
     bool launched = false;
 #if defined(HK_MUL2) && !defined(HK_NO_G2_PAIR)
-    // An Fq2 point addition split over a lane pair (field.cuh Fp2Half): bit-identical, 230 registers without spills
-    // (the one-thread kernel: 255 with 1 KB of spills), multiplier pipe 81.9 % vs 72.1 % busy in the `ncu --set full`
-    // captures at 2^18 (profiles/r02p_*): 4.64 vs 5.16 ms.  Measured standalone (G2 MSM, ms, pair vs one thread):
-    // 2^16 2.77 / 2.86, 2^17 4.40 / 4.73, 2^18 6.42 / 6.97, 2^19 11.42 / 11.36, 2^20 21.33 / 21.07 -- the gain is gone
-    // once the window table passes ~1 GB, so the default (HK_OPT_G2_LANE_PAIR = 0) picks it for base sets of up to
-    // 5 M table entries (2^18 points x 16 windows: every proof shape but VM), whatever the batch; 1 = always,
-    // 2 = never.  Proof pipeline: +1 %.
+    // An Fq2 point addition split over a lane pair (field.cuh Fp2Half): bit-identical, no spills (the one-thread kernel:
+    // 255 registers with 1 KB of spills), multiplier pipe 81.9 % vs 72.1 % busy in the `ncu --set full` captures at
+    // 2^18 (profiles/r02p_*): 4.64 vs 5.16 ms.  Standalone G2 MSM, ms, pair vs one thread: 2^16 2.57 / 2.67,
+    // 2^18 6.11 / 6.71, 2^20 20.79 / 20.79, 2^22 73.3 / 74.1; proof pipeline +1 %.  Default for every field with the
+    // fused dual product (BLS12-381); HK_OPT_G2_LANE_PAIR = 2 selects the one-thread kernel.
     if constexpr (GROUP == 2) {
         if constexpr (F::base::HAS_MUL2) {
-            const size_t entries = so.table ? (size_t)bv.n_total * (size_t)pl.W : (size_t)bv.n_total;
-            if (ctx->opt_g2_pair == 1 || (ctx->opt_g2_pair == 0 && entries <= 5000000)) {
+            if (ctx->opt_g2_pair != 2) {
                 k_msm_accum_g2pair<F, 2><<<ceil_div(2 * (size_t)nthr0, 128), 128, 0, sb>>>(d_bases, so.pairs, so.d_count, s_min,
                                                                                         buckets, partial, partial_keys, nthr0);
                 launched = true;

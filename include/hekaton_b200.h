@@ -107,8 +107,7 @@ int32_t hk_ctx_destroy(hk_ctx* ctx);
  *   HK_OPT_SORT_GLOBAL_ATOMICS  1 = always sort the digits with the global-atomic kernels (default 0: base sets with a
  *                         window table use block-private shared-memory histograms)
  *   HK_OPT_G2_LANE_PAIR   G2 bucket accumulation with every Fq2 value spread over a lane pair (BLS12-381 only):
- *                         0 = automatic (default: base sets of up to 5 M window-table entries, i.e. tables below
- *                         ~1 GB, where it measures 3-8 % faster), 1 = always, 2 = never (one thread per addition)
+ *                         0 / 1 = on (default: 0-9 % faster at every size), 2 = off (one thread per point addition)
  *   HK_OPT_QUAD_MAX_THREADS  fold / reduction / tree-sum launches of at most this many logical threads run with four
  *                         lanes per point addition (default 32768 for a standalone MSM, never inside a proof
  *                         batch; 1 = never)
