@@ -33,6 +33,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "fold_runs.cuh"
 
 namespace hk {
 
@@ -331,7 +332,6 @@ inline void exclusive_scan_u32(hk_ctx* ctx, MsmWs& ws, cudaStream_t st, uint32_t
 // S = max(s_min, ceil(count / nthreads)) computed from the device-side item count.  Runs strictly inside the
 // segment are complete -> bucket array.  The first and the last run of a segment may continue in a
 // neighbour -> partial list slots 2t, 2t+1 (key = 0xffffffff marks an empty slot).
-static constexpr uint32_t KEY_NONE = 0xffffffffu;
 
 template <class F, int MINB>
 __global__ void __launch_bounds__(128, MINB)
@@ -623,42 +623,8 @@ k_msm_fold_quad(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_
 // most two) runs that start in thread i's slots; k_msm_fold_check raises a flag if any run has three or more pieces
 // (a thread whose whole range lies inside one bucket's run: skewed scalars) or if the list has a hole before its end;
 // k_msm_fold_resolve_quad closes every run when the flag is clear, and the remaining fold levels return at once
-// (`gate`).  With the flag set nothing is written and the levels run as before.
-struct FoldRuns {
-    bool a, a_merge, b, b_merge, bad;      // run A starts at F_i (pieces F_i [, F_{i+1}]); run B at L_i ([, F_{i+1}])
-    uint32_t ka, kb;
-};
-
-__device__ __forceinline__ FoldRuns fold_runs(const uint32_t* __restrict__ keys, uint32_t i, uint32_t n) {
-    FoldRuns r{false, false, false, false, false, KEY_NONE, KEY_NONE};
-    const uint32_t k0 = keys[2 * i], k1 = keys[2 * i + 1];
-    const uint32_t nk0 = i + 1 < n ? keys[2 * i + 2] : KEY_NONE, nk1 = i + 1 < n ? keys[2 * i + 3] : KEY_NONE;
-    if (k0 == KEY_NONE) {                  // empty thread: legal only past the end of the list
-        r.bad = (k1 != KEY_NONE) || (nk0 != KEY_NONE);
-        return r;
-    }
-    uint32_t prev = KEY_NONE;              // key of the piece in front of F_i
-    if (i > 0) {
-        prev = keys[2 * i - 1];
-        if (prev == KEY_NONE) prev = keys[2 * i - 2];
-    }
-    const uint32_t nnk0 = i + 2 < n ? keys[2 * i + 4] : KEY_NONE;
-    const bool next_single = nk0 != KEY_NONE && nk1 == KEY_NONE;      // thread i+1 holds one piece only
-    r.ka = k0;
-    r.kb = k1;
-    if (k1 != KEY_NONE) {
-        r.a = prev != k0;                  // F_i alone (L_i has another key)
-        r.b = true;
-        r.b_merge = nk0 == k1;
-        r.bad = r.b_merge && next_single && nnk0 == k1;
-    } else if (prev != k0) {
-        r.a = true;
-        r.a_merge = nk0 == k0;
-        r.bad = r.a_merge && next_single && nnk0 == k0;
-    }
-    return r;
-}
-
+// (`gate`).  With the flag set nothing is written and the levels run as before.  fold_runs lives in fold_runs.cuh so
+// that tests/test_fold_runs_host.py can fuzz it on the CPU against a brute-force grouping of the pieces.
 static __global__ void k_msm_fold_check(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* flag) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
